@@ -1,0 +1,182 @@
+// K4 beta-binomial alignment prior, K5 pitch-statistics partials, K6 FilterbankFeatures normalise/mask.
+#pragma once
+#include "common.cuh"
+#include "../../include/roar_sup.h"
+
+namespace roar {
+
+// ------------------------------------------------------------------------------------ K4 prior
+// Replaces beta_binomial_prior_distribution (tts/parts/utils/tts_dataset_utils.py:128-149):
+//   P[y-1, k] = exp( lnC(n,k) + lnB(k+a, n-k+b) - lnB(a,b) ),  n=N-1, a=s*y, b=s*(M+1-y), y=1..M, k=0..N-1
+// With the scaling factor s == 1 every gammaln argument is a positive integer, so the whole
+// expression is a sum of nine log-factorials LF[i] = ln(i!) looked up in a float64 table built once
+// per handle (L1/L2 resident); the reference's float32 gammaln noise (~1e-3 relative) is not
+// reproduced -- the float64 value is rounded once.  Output is write-bound: 4*M*N bytes.
+struct PriorParams {
+  const int32_t* text_len;
+  const int32_t* mel_len;
+  const int64_t* out_off;
+  float* out;
+  const double* lf;       // ln(i!) for i < lf_n
+  int32_t lf_n;
+  int32_t utt_base;       // utterance index of blockIdx.y == 0
+  int32_t rows_per_cta;
+  double scaling;
+};
+
+HD double prior_lf(const PriorParams& p, int i) { return i < p.lf_n ? p.lf[i] : lgamma((double)i + 1.0); }
+
+HD float prior_value_int(const PriorParams& p, int N, int M, int y, int k) {
+  const int n = N - 1;
+  const double lc = prior_lf(p, n) - prior_lf(p, k) - prior_lf(p, n - k);
+  const double lb1 = prior_lf(p, k + y - 1) + prior_lf(p, n - k + M - y) - prior_lf(p, n + M);
+  const double lb2 = prior_lf(p, y - 1) + prior_lf(p, M - y) - prior_lf(p, M);
+  return (float)exp(lc + lb1 - lb2);
+}
+HD float prior_value_real(const PriorParams& p, int N, int M, int y, int k) {
+  const double n = N - 1, a = p.scaling * y, b = p.scaling * (M + 1 - y);
+  const double lc = lgamma(n + 1) - lgamma(k + 1.0) - lgamma(n - k + 1);
+  const double lb1 = lgamma(k + a) + lgamma(n - k + b) - lgamma(n + a + b);
+  const double lb2 = lgamma(a) + lgamma(b) - lgamma(a + b);
+  return (float)exp(lc + lb1 - lb2);
+}
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(256) k_align_prior(const PriorParams p) {
+  const int utt = p.utt_base + blockIdx.y;
+  const int N = p.text_len[utt], M = p.mel_len[utt];
+  const int r0 = blockIdx.x * p.rows_per_cta;
+  if (r0 >= M || N <= 0) return;
+  const int r1 = r0 + p.rows_per_cta < M ? r0 + p.rows_per_cta : M;
+  float* out = p.out + p.out_off[utt];
+  const int64_t e0 = (int64_t)r0 * N, e1 = (int64_t)r1 * N;
+  const bool integer = p.scaling == 1.0;
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int m = (int)(e / N), k = (int)(e - (int64_t)m * N);
+    out[e] = integer ? prior_value_int(p, N, M, m + 1, k) : prior_value_real(p, N, M, m + 1, k);
+  }
+}
+
+// ------------------------------------------------------------------------------------ K5 stats
+// get_pitch_stats (scripts/dataset_processing/tts/extract_sup_data.py:8-13): mean / unbiased std /
+// min / max over pitch != 0.  Produces float64 partials (sum, sumsq, count, min, max) that the ranks
+// all-reduce.  min/max use the unsigned-integer order of positive doubles.
+__device__ __forceinline__ void stats_merge(double* out5, double s, double q, double c, double mn, double mx) {
+  if (c > 0) {
+    atomicAdd(&out5[0], s);
+    atomicAdd(&out5[1], q);
+    atomicAdd(&out5[2], c);
+    atomicMin((unsigned long long*)&out5[3], (unsigned long long)__double_as_longlong(mn));
+    atomicMax((unsigned long long*)&out5[4], (unsigned long long)__double_as_longlong(mx));
+  }
+}
+__device__ __forceinline__ void stats_warp_reduce(double& s, double& q, double& c, double& mn, double& mx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+}
+__global__ void k_stats_init(double* out, int n_groups) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_groups) {
+    out[i * 5 + 0] = 0; out[i * 5 + 1] = 0; out[i * 5 + 2] = 0;
+    out[i * 5 + 3] = __longlong_as_double(0x7FF0000000000000LL);  // +inf
+    out[i * 5 + 4] = 0;
+  }
+}
+__global__ void __launch_bounds__(256) k_pitch_partials(const float* f0, int64_t n, double* out5) {
+  double s = 0, q = 0, c = 0, mn = __longlong_as_double(0x7FF0000000000000LL), mx = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = f0[i];
+    if (v != 0.f) { const double d = v; s += d; q += d * d; c += 1; mn = fmin(mn, d); mx = fmax(mx, d); }
+  }
+  stats_warp_reduce(s, q, c, mn, mx);
+  __shared__ double sh[5][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = q; sh[2][warp] = c; sh[3][warp] = mn; sh[4][warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    s = lane < nw ? sh[0][lane] : 0; q = lane < nw ? sh[1][lane] : 0; c = lane < nw ? sh[2][lane] : 0;
+    mn = lane < nw ? sh[3][lane] : __longlong_as_double(0x7FF0000000000000LL);
+    mx = lane < nw ? sh[4][lane] : 0;
+    stats_warp_reduce(s, q, c, mn, mx);
+    if (lane == 0) stats_merge(out5, s, q, c, mn, mx);
+  }
+}
+// per-utterance groups (speaker ids): one warp per utterance, one merge per utterance
+__global__ void __launch_bounds__(256) k_pitch_partials_grouped(const float* f0, const int64_t* frame_off,
+                                                                const int32_t* group, int32_t n_utts,
+                                                                int32_t n_groups, double* out) {
+  const int utt = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (utt >= n_utts) return;
+  const int g = group[utt];
+  double s = 0, q = 0, c = 0, mn = __longlong_as_double(0x7FF0000000000000LL), mx = 0;
+  for (int64_t i = frame_off[utt] + lane; i < frame_off[utt + 1]; i += 32) {
+    const float v = f0[i];
+    if (v != 0.f) { const double d = v; s += d; q += d * d; c += 1; mn = fmin(mn, d); mx = fmax(mx, d); }
+  }
+  stats_warp_reduce(s, q, c, mn, mx);
+  if (lane == 0 && g >= 0 && g < n_groups) stats_merge(out + (size_t)g * 5, s, q, c, mn, mx);
+}
+
+// ------------------------------------------------------------------------------------ K6 normalise
+// normalize_batch + masked_fill + pad (features.py:25-61, 444-460) on out[B, n_mels, Tpad], in place.
+struct NormParams {
+  float* x;
+  const int64_t* seq_len;   // frames valid per utterance
+  int32_t B, n_mels, T_full, Tpad, mode;
+  float pad_value;
+};
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+  return t;
+}
+// grid = (n_mels, B) for per_feature / none, (1, B) for all_features
+__global__ void __launch_bounds__(256) k_fbank_normalize(const NormParams p) {
+  __shared__ double sh[8];
+  const int b = blockIdx.y;
+  int64_t n = p.seq_len[b];
+  if (n > p.T_full) n = p.T_full;
+  if (n < 0) n = 0;
+  const int rows = p.mode == ROAR_NORM_ALL_FEATURES ? p.n_mels : 1;
+  float* base = p.x + ((size_t)b * p.n_mels + (p.mode == ROAR_NORM_ALL_FEATURES ? 0 : blockIdx.x)) * p.Tpad;
+  double mean = 0, inv = 1;
+  if (p.mode != ROAR_NORM_NONE) {
+    double s = 0;
+    for (int r = 0; r < rows; ++r)
+      for (int64_t t = threadIdx.x; t < n; t += blockDim.x) s += base[(size_t)r * p.Tpad + t];
+    const double cnt = (double)n * rows;
+    mean = block_sum(s, sh) / cnt;
+    double q = 0;
+    for (int r = 0; r < rows; ++r)
+      for (int64_t t = threadIdx.x; t < n; t += blockDim.x) { const double d = base[(size_t)r * p.Tpad + t] - mean; q += d * d; }
+    const double var = block_sum(q, sh) / (cnt - 1.0);
+    // reference: float32 mean/std, std += 1e-5
+    const float stdf = (float)sqrt(var) + 1e-5f;
+    inv = 1.0;
+    const float meanf = (float)mean;
+    for (int r = 0; r < rows; ++r)
+      for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
+        float* px = base + (size_t)r * p.Tpad + t;
+        *px = (*px - meanf) / stdf;
+      }
+  }
+  (void)inv;
+  for (int r = 0; r < rows; ++r)
+    for (int64_t t = n + threadIdx.x; t < p.Tpad; t += blockDim.x) base[(size_t)r * p.Tpad + t] = p.pad_value;
+}
+#endif  // __CUDACC__
+
+}  // namespace roar

@@ -1,0 +1,375 @@
+// K1  stft_mel_energy: reflect-padded framed STFT (shared-memory Stockham real FFT over a window
+// table) fused with |X|, the sparse banded mel projection, log guard and per-frame L2 energy.
+//
+// Replaces (reference paths): TTSDataset.get_spec / get_log_mel / energy
+//   roar/collections/tts/data/dataset.py:324-333, 524-537, 751-753
+// and the STFT..log part of FilterbankFeatures.forward
+//   roar/collections/asr/parts/preprocessing/features.py:384-434.
+//
+// Work decomposition: one CTA = one tile of FT consecutive frames of one utterance.  The tile's
+// audio span ((FT-1)*hop + n_fft samples) is staged once in shared memory -- by ONE 1-D TMA bulk
+// copy (cp.async.bulk + mbarrier) when the span is interior and 16-B aligned, by mirrored
+// per-thread loads at the utterance edges -- so every sample is read from HBM/L2 once per tile.
+// P = M/8 threads own a frame (M = n_fft/2 complex points, radix-8 Stockham passes, real-FFT
+// untangle), G = blockDim/P frames are in flight per pass.  The result tile [n_mels, FT] is
+// staged in shared memory and written as row segments (coalesced).
+//
+// Algorithmic HBM bytes per frame: 4*hop in + 4*(n_mels+1) out.
+#pragma once
+#include "common.cuh"
+#include "fft.cuh"
+#include "../../include/roar_sup.h"
+
+namespace roar {
+
+struct StftParams {
+  // batch
+  const float* audio;
+  const int64_t* sample_off;
+  const int32_t* sample_len;
+  const int64_t* frame_off;   // [n_utts+1]
+  const int32_t* tile_off;    // [n_utts+1] prefix sum of ceil(T_i / FT)
+  int32_t n_utts;
+  float* logmel;              // may be null
+  float* energy;              // may be null
+  int64_t out_utt_stride;     // 0 => ragged: block of utterance i starts at n_mels*frame_off[i], row stride T_i
+  int64_t out_row_stride;
+  // geometry
+  int32_t n_fft, hop, M, n_bins, n_mels, FT, span, pad_left;
+  int32_t P, G;               // threads per frame, frames in flight
+  // options
+  float floor_, mag_power, log_guard, preemph;
+  int32_t log_mode, has_preemph, use_tma;
+  // tables (device memory)
+  const float* window;        // [n_fft]
+  const cf32* tw;             // [M]    W_M^k
+  const cf32* tw_post;        // [M+1]  W_{n_fft}^k
+  const int32_t* mel_start;   // [n_mels]
+  const int32_t* mel_count;
+  const int32_t* mel_offset;
+  const float* mel_w;         // packed band weights
+  int32_t mel_nw;
+};
+
+// shared-memory carve-up (all offsets in bytes, 16-B aligned)
+struct StftSmem {
+  float* audio;     // [span]
+  float* window;    // [n_fft]
+  cf32* tw;         // [M]
+  cf32* tw_post;    // [M+1]
+  cf32* bufA;       // [G*M]
+  cf32* bufB;       // [G*M]   (spec[G][n_bins] float aliases the buffer not holding the FFT result)
+  float* part;      // [blockDim] energy partials
+  float* out;       // [n_mels][FT+1] staging
+  float* en;        // [FT]
+  int32_t* mel_start; int32_t* mel_count; int32_t* mel_offset;  // [n_mels]
+  float* mel_w;     // [mel_nw]
+  unsigned long long* mbar;
+};
+
+HD size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+HD size_t stft_smem_carve(const StftParams& p, int nthreads, unsigned char* base, StftSmem* s) {
+  size_t o = 0;
+#define CARVE(field, type, count) { if (s) s->field = (type*)(base + o); o = align16(o + sizeof(type) * (size_t)(count)); }
+  CARVE(mbar, unsigned long long, 2)
+  CARVE(audio, float, p.span)
+  CARVE(window, float, p.n_fft)
+  CARVE(tw, cf32, p.M)
+  CARVE(tw_post, cf32, p.M + 1)
+  CARVE(bufA, cf32, (size_t)p.G * p.M + 8)
+  CARVE(bufB, cf32, (size_t)p.G * p.M + 8)
+  CARVE(part, float, nthreads)
+  CARVE(out, float, (size_t)p.n_mels * (p.FT + 1))
+  CARVE(en, float, p.FT)
+  CARVE(mel_start, int32_t, p.n_mels)
+  CARVE(mel_count, int32_t, p.n_mels)
+  CARVE(mel_offset, int32_t, p.n_mels)
+  CARVE(mel_w, float, p.mel_nw)
+#undef CARVE
+  return o;
+}
+
+struct StftTile {
+  int32_t utt, t0, T, nf;     // frames [t0, t0+nf) of utterance utt with T frames
+  int64_t off; int32_t L;
+  int64_t p0;                 // unpadded sample position of span[0] (may be negative)
+};
+
+// locate the tile: binary search of blockIdx in tile_off
+HD bool stft_locate(const StftParams& p, int tile, StftTile* t) {
+  int lo = 0, hi = p.n_utts;
+  if (tile >= p.tile_off[p.n_utts]) return false;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (p.tile_off[mid] <= tile) lo = mid; else hi = mid;
+  }
+  t->utt = lo;
+  t->T = (int32_t)(p.frame_off[lo + 1] - p.frame_off[lo]);
+  t->t0 = (tile - p.tile_off[lo]) * p.FT;
+  t->nf = t->T - t->t0 < p.FT ? t->T - t->t0 : p.FT;
+  t->off = p.sample_off[lo];
+  t->L = p.sample_len[lo];
+  t->p0 = (int64_t)t->t0 * p.hop - p.pad_left;
+  return true;
+}
+
+HD float stft_sample(const StftParams& p, const StftTile& t, int64_t pos) {
+  // reflect (no edge repeat) into [0, L)
+  int64_t q = pos;
+  const int64_t L = t.L;
+  if (q < 0) q = -q;
+  if (q >= L) q = 2 * (L - 1) - q;
+  if (q < 0 || q >= L) return 0.f;  // only reachable when L <= pad (rejected by the host)
+  float v = p.audio[t.off + q];
+  if (p.has_preemph && q >= 1) v = v - p.preemph * p.audio[t.off + q - 1];
+  return v;
+}
+
+// ---- phase A: tables + audio tile (generic path; the TMA path replaces the audio part on device)
+HD void stft_phase_tables(const StftParams& p, StftSmem& s, int tid, int nthr) {
+  for (int i = tid; i < p.n_fft; i += nthr) s.window[i] = p.window[i];
+  for (int i = tid; i < p.M; i += nthr) s.tw[i] = p.tw[i];
+  for (int i = tid; i <= p.M; i += nthr) s.tw_post[i] = p.tw_post[i];
+  for (int i = tid; i < p.n_mels; i += nthr) {
+    s.mel_start[i] = p.mel_start[i]; s.mel_count[i] = p.mel_count[i]; s.mel_offset[i] = p.mel_offset[i];
+  }
+  for (int i = tid; i < p.mel_nw; i += nthr) s.mel_w[i] = p.mel_w[i];
+}
+
+HD void stft_phase_audio(const StftParams& p, const StftTile& t, StftSmem& s, int tid, int nthr,
+                         int lo, int hi) {
+  // fill span indices [lo, hi)
+  for (int i = lo + tid; i < hi; i += nthr) s.audio[i] = stft_sample(p, t, t.p0 + i);
+}
+
+// ---- phase B1: window + first radix pass straight from the audio tile
+template <int R>
+HD void stft_first_pass(const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid) {
+  const int slot = tid / p.P, u = tid - slot * p.P;
+  const int f = g * p.G + slot;
+  if (f >= t.nf) return;
+  const float* a = s.audio + f * p.hop;
+  cf32* out = s.bufA + (size_t)slot * p.M;
+  const int nb = p.M / R;
+  for (int j = u; j < nb; j += p.P) {
+    cf32 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int n = j + r * nb;
+      v[r].x = a[2 * n] * s.window[2 * n];
+      v[r].y = a[2 * n + 1] * s.window[2 * n + 1];
+    }
+    dftR<R, false>(v);
+    stockham_store<R>(v, out, 1, j);
+  }
+}
+
+template <int R>
+HD void stft_pass(const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid, int Ns,
+                  const cf32* in_base, cf32* out_base) {
+  const int slot = tid / p.P, u = tid - slot * p.P;
+  const int f = g * p.G + slot;
+  if (f >= t.nf) return;
+  const cf32* in = in_base + (size_t)slot * p.M;
+  cf32* out = out_base + (size_t)slot * p.M;
+  const int nb = p.M / R;
+  for (int j = u; j < nb; j += p.P) {
+    cf32 v[R];
+    stockham_load<R>(v, in, p.M, j);
+    stockham_twiddle_dft<R, false>(v, p.M, Ns, j, s.tw);
+    stockham_store<R>(v, out, Ns, j);
+  }
+}
+
+HD float stft_pow(float mag, float power) {
+  if (power == 1.0f) return mag;
+  if (power == 2.0f) return mag * mag;
+  return powf(mag, power);
+}
+
+// ---- untangle the real FFT, magnitude (+ floor), power, energy partials
+HD void stft_phase_post(const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid,
+                        const cf32* z_base, float* spec_base) {
+  const int slot = tid / p.P, u = tid - slot * p.P;
+  const int f = g * p.G + slot;
+  float esum = 0.f;
+  if (f < t.nf) {
+    const cf32* Z = z_base + (size_t)slot * p.M;
+    float* spec = spec_base + (size_t)slot * (2 * p.M);
+    for (int k = u; k <= p.M; k += p.P) {
+      const cf32 zk = Z[k & (p.M - 1)];
+      const cf32 zc = cconj(Z[(p.M - k) & (p.M - 1)]);
+      // X[k] = (zk+zc)/2 + W_N^k * (zk-zc)/(2i)
+      cf32 e; e.x = 0.5f * (zk.x + zc.x); e.y = 0.5f * (zk.y + zc.y);
+      cf32 d; d.x = 0.5f * (zk.y - zc.y); d.y = -0.5f * (zk.x - zc.x);   // (zk-zc)/(2i)
+      const cf32 w = s.tw_post[k];
+      const float re = e.x + (w.x * d.x - w.y * d.y);
+      const float im = e.y + (w.x * d.y + w.y * d.x);
+      const float mag = sqrtf(re * re + im * im + p.floor_);
+      esum += mag * mag;
+      spec[k] = stft_pow(mag, p.mag_power);
+    }
+  }
+  s.part[tid] = esum;
+}
+
+// ---- sparse mel rows + log guard (+ the energy reduction as extra work items)
+HD void stft_phase_mel(const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid, int nthr,
+                       const float* spec_base) {
+  const int per = p.n_mels + 1;
+  for (int w = tid; w < p.G * per; w += nthr) {
+    const int slot = w / per, m = w - slot * per;
+    const int f = g * p.G + slot;
+    if (f >= t.nf) continue;
+    if (m == p.n_mels) {
+      float e = 0.f;
+      const float* pp = s.part + slot * p.P;
+      for (int i = 0; i < p.P; ++i) e += pp[i];
+      s.en[f] = sqrtf(e);
+      continue;
+    }
+    const float* spec = spec_base + (size_t)slot * (2 * p.M) + s.mel_start[m];
+    const float* wgt = s.mel_w + s.mel_offset[m];
+    const int cnt = s.mel_count[m];
+    float acc = 0.f;
+    for (int c = 0; c < cnt; ++c) acc += wgt[c] * spec[c];
+    if (p.log_mode == ROAR_LOG_CLAMP) acc = logf(acc < p.log_guard ? p.log_guard : acc);
+    else if (p.log_mode == ROAR_LOG_ADD) acc = logf(acc + p.log_guard);
+    s.out[m * (p.FT + 1) + f] = acc;
+  }
+}
+
+HD void stft_phase_store(const StftParams& p, const StftTile& t, StftSmem& s, int tid, int nthr) {
+  if (p.logmel) {
+    const int64_t base = p.out_utt_stride ? (int64_t)t.utt * p.out_utt_stride
+                                          : (int64_t)p.n_mels * p.frame_off[t.utt];
+    const int64_t rs = p.out_row_stride ? p.out_row_stride : t.T;
+    for (int i = tid; i < p.n_mels * p.FT; i += nthr) {
+      const int m = i / p.FT, f = i - m * p.FT;
+      if (f < t.nf) p.logmel[base + (int64_t)m * rs + t.t0 + f] = s.out[m * (p.FT + 1) + f];
+    }
+  }
+  if (p.energy) {
+    for (int f = tid; f < t.nf; f += nthr) p.energy[p.frame_off[t.utt] + t.t0 + f] = s.en[f];
+  }
+}
+
+// One FFT pass of radix R over all frames in flight (dispatch on the runtime radix).
+HD void stft_pass_any(int R, const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid,
+                      int Ns, const cf32* src, cf32* dst) {
+  if (R == 8) stft_pass<8>(p, t, s, g, tid, Ns, src, dst);
+  else if (R == 4) stft_pass<4>(p, t, s, g, tid, Ns, src, dst);
+  else stft_pass<2>(p, t, s, g, tid, Ns, src, dst);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) k_stft_mel(const StftParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StftSmem s;
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  stft_smem_carve(p, nthr, smem_raw, &s);
+  StftTile t;
+  if (!stft_locate(p, blockIdx.x, &t)) return;
+
+  // ---- audio tile: one TMA bulk copy for the 16-B aligned interior, mirrored loads for the rest
+  const int64_t need_lo = t.p0, need_hi = t.p0 + (int64_t)(t.nf - 1) * p.hop + p.n_fft;  // [lo, hi)
+  int lo_i = 0, hi_i = (int)(need_hi - need_lo);     // span indices to fill
+  int tma_lo = 0, tma_hi = 0;                        // span indices covered by the bulk copy
+  if (p.use_tma && !p.has_preemph) {
+    int64_t a = need_lo < 0 ? 0 : need_lo, b = need_hi > t.L ? t.L : need_hi;
+    // 16-B alignment of both the global source and the shared destination
+    const int64_t g0 = t.off + a;
+    int64_t a4 = a + ((4 - (g0 & 3)) & 3);
+    if (((a4 - need_lo) & 3) != 0) a4 = b;           // destination not alignable: skip TMA
+    int64_t b4 = a4 + ((b - a4) & ~(int64_t)3);
+    if (b4 - a4 >= 64 && ((reinterpret_cast<uintptr_t>(p.audio) & 15) == 0)) {
+      tma_lo = (int)(a4 - need_lo); tma_hi = (int)(b4 - need_lo);
+    }
+  }
+  if (tma_hi > tma_lo) {
+    const unsigned bar = smem_u32(s.mbar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned bytes = (unsigned)(tma_hi - tma_lo) * 4u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(s.audio + tma_lo)),
+          "l"(p.audio + t.off + (need_lo + tma_lo)), "r"(bytes), "r"(bar)
+          : "memory");
+    }
+    stft_phase_tables(p, s, tid, nthr);
+    stft_phase_audio(p, t, s, tid, nthr, lo_i, tma_lo);
+    stft_phase_audio(p, t, s, tid, nthr, tma_hi, hi_i);
+    // wait for the bulk copy (phase parity 0)
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+          : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
+  } else {
+    stft_phase_tables(p, s, tid, nthr);
+    stft_phase_audio(p, t, s, tid, nthr, lo_i, hi_i);
+  }
+  __syncthreads();
+
+  const int n_groups = (t.nf + p.G - 1) / p.G;
+  for (int g = 0; g < n_groups; ++g) {
+    stft_first_pass<8>(p, t, s, g, tid);
+    __syncthreads();
+    const FftPlan plan = make_plan(p.M);
+    int Ns = plan.radix[0];
+    const cf32* src = s.bufA;
+    cf32* dst = s.bufB;
+    for (int ps = 1; ps < plan.n_pass; ++ps) {
+      stft_pass_any(plan.radix[ps], p, t, s, g, tid, Ns, src, dst);
+      __syncthreads();
+      Ns *= plan.radix[ps];
+      const cf32* tmp = src; src = dst; dst = const_cast<cf32*>(tmp);
+    }
+    const cf32* zfin = src;            // FFT result
+    float* spec = (float*)dst;         // the other buffer holds |X| for the mel phase
+    stft_phase_post(p, t, s, g, tid, zfin, spec);
+    __syncthreads();
+    stft_phase_mel(p, t, s, g, tid, nthr, spec);
+    __syncthreads();
+  }
+  stft_phase_store(p, t, s, tid, nthr);
+}
+
+// prefix sum of ceil(T_i/FT) -> tile_off[n_utts+1]; one CTA
+__global__ void k_tile_offsets(const int64_t* frame_off, int32_t n_utts, int32_t FT, int32_t* tile_off) {
+  __shared__ int32_t s_carry;
+  __shared__ int32_t s_scan[1024];
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_carry = 0; tile_off[0] = 0; }
+  __syncthreads();
+  for (int base = 0; base < n_utts; base += 1024) {
+    const int i = base + tid;
+    int32_t v = 0;
+    if (i < n_utts) { int64_t T = frame_off[i + 1] - frame_off[i]; v = (int32_t)((T + FT - 1) / FT); }
+    s_scan[tid] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      int32_t x = tid >= d ? s_scan[tid - d] : 0;
+      __syncthreads();
+      s_scan[tid] += x;
+      __syncthreads();
+    }
+    if (i < n_utts) tile_off[i + 1] = s_carry + s_scan[tid];
+    __syncthreads();
+    if (tid == 1023) s_carry += s_scan[1023];
+    __syncthreads();
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace roar

@@ -1,0 +1,524 @@
+// libroar_sup.so -- C ABI (include/roar_sup.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/roar_sup.h"
+#include "common.cuh"
+#include "fft.cuh"
+#include "k_misc.cuh"
+#include "k_pyin_front.cuh"
+#include "k_stft_mel.cuh"
+#include "k_viterbi.cuh"
+#include "tables.hpp"
+
+using namespace roar;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ROAR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+
+struct roar_sup_handle {
+  roar_sup_config cfg;
+  Geometry g;
+  int device = 0;
+  int sm_count = 148;
+  size_t max_smem = 0;
+  std::vector<void*> allocs;
+  // K1
+  float* d_window = nullptr; cf32* d_tw = nullptr; cf32* d_tw_post = nullptr;
+  int32_t *d_mel_start = nullptr, *d_mel_count = nullptr, *d_mel_offset = nullptr;
+  float* d_mel_w = nullptr; int mel_nw = 0;
+  int stft_FT = 16, stft_P = 64, stft_G = 4, stft_span = 0; size_t stft_smem = 0;
+  int use_tma = 1;
+  // K2
+  cf64* d_tw64 = nullptr;
+  double *d_thr = nullptr, *d_beta = nullptr, *d_beta_cum = nullptr, *d_bexp = nullptr, *d_bfact = nullptr;
+  int pyin_FT = 16, pyin_P = 128, pyin_G = 2, pyin_span = 0; size_t cmnd_smem = 0, prob_smem = 0;
+  // K3
+  double* d_lt_rows = nullptr; uint16_t* d_row_id = nullptr; double* d_freqs = nullptr;
+  int n_rows = 0; double lt0 = 0, li_v = 0, li_u = 0;
+  int vit_threads = 0; size_t vit_smem = 0; int lt_in_smem = 1;
+  // K4
+  double* d_lf = nullptr; int lf_n = 0;
+  // optional per-kernel timing (diagnostics; not thread-safe)
+  int profiling = 0;
+  struct Pending { int id; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  double prof_ms[ROAR_K_COUNT] = {0};
+  int64_t prof_n[ROAR_K_COUNT] = {0};
+};
+
+static cudaEvent_t prof_event(roar_sup_handle* h) {
+  if (!h->pool.empty()) { cudaEvent_t e = h->pool.back(); h->pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+// LAUNCH(h, id, stream, kernel<<<...>>>(...)) -- brackets the launch with events when profiling is on
+#define LAUNCH(h, kid, st, ...)                                             \
+  do {                                                                     \
+    if ((h)->profiling) {                                                  \
+      roar_sup_handle::Pending pe_; pe_.id = (kid);                        \
+      pe_.a = prof_event(h); pe_.b = prof_event(h);                        \
+      cudaEventRecord(pe_.a, st);                                          \
+      __VA_ARGS__;                                                         \
+      cudaEventRecord(pe_.b, st);                                          \
+      (h)->pending.push_back(pe_);                                         \
+    } else {                                                               \
+      __VA_ARGS__;                                                         \
+    }                                                                      \
+  } while (0)
+
+template <class T> static int upload(roar_sup_handle* h, const std::vector<T>& v, T** out) {
+  void* p = nullptr;
+  size_t bytes = v.size() * sizeof(T);
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(ROAR_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  h->allocs.push_back(p);
+  if (!v.empty()) {
+    e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(ROAR_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+  }
+  *out = (T*)p;
+  return 0;
+}
+
+static StftParams stft_params_base(const roar_sup_handle* h) {
+  StftParams p;
+  memset(&p, 0, sizeof(p));
+  const Geometry& g = h->g;
+  p.n_fft = g.n_fft; p.hop = g.hop; p.M = g.M; p.n_bins = g.n_bins; p.n_mels = g.n_mels;
+  p.FT = h->stft_FT; p.span = h->stft_span; p.P = h->stft_P; p.G = h->stft_G;
+  p.pad_left = h->cfg.exact_pad ? (g.n_fft - g.hop) / 2 : g.n_fft / 2;
+  p.floor_ = (float)h->cfg.spec_floor; p.mag_power = (float)h->cfg.mag_power;
+  p.log_guard = (float)h->cfg.log_guard; p.preemph = (float)h->cfg.preemph;
+  p.log_mode = h->cfg.log_mode; p.has_preemph = h->cfg.has_preemph; p.use_tma = h->use_tma;
+  p.window = h->d_window; p.tw = h->d_tw; p.tw_post = h->d_tw_post;
+  p.mel_start = h->d_mel_start; p.mel_count = h->d_mel_count; p.mel_offset = h->d_mel_offset;
+  p.mel_w = h->d_mel_w; p.mel_nw = h->mel_nw;
+  return p;
+}
+
+static PyinParams pyin_params_base(const roar_sup_handle* h) {
+  PyinParams p;
+  memset(&p, 0, sizeof(p));
+  const Geometry& g = h->g;
+  p.F = g.pf; p.W = g.pw; p.hop = g.ph; p.H = g.pf / 2;
+  p.min_period = g.min_period; p.max_period = g.max_period; p.n_lags = g.n_lags;
+  p.FT = h->pyin_FT; p.span = h->pyin_span; p.P = h->pyin_P; p.G = h->pyin_G;
+  p.npb = g.npb; p.nbps = g.nbps; p.kmax = g.kmax; p.n_thr = g.n_thr;
+  p.sr = h->cfg.sample_rate; p.fmin = h->cfg.pitch_fmin; p.no_trough_prob = h->cfg.no_trough_prob;
+  p.tw = h->d_tw64; p.thresholds = h->d_thr; p.beta_probs = h->d_beta; p.beta_cum = h->d_beta_cum;
+  p.boltz_exp = h->d_bexp; p.boltz_fact = h->d_bfact;
+  return p;
+}
+
+extern "C" {
+
+int roar_sup_abi_version(void) { return ROAR_SUP_ABI_VERSION; }
+const char* roar_sup_last_error(void) { return g_err.c_str(); }
+
+void roar_sup_config_default(roar_sup_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(*c);
+  c->sample_rate = 22050; c->n_fft = 1024; c->win_length = 1024; c->hop_length = 256;
+  c->window = ROAR_WIN_HANN; c->n_mels = 80; c->mel_norm = 1; c->fmin = 0.0; c->fmax = 8000.0;
+  c->spec_floor = 1e-9; c->mag_power = 1.0; c->log_mode = ROAR_LOG_CLAMP; c->exact_pad = 0;
+  c->log_guard = 1.17549435e-38; c->has_preemph = 0; c->normalize = ROAR_NORM_NONE; c->preemph = 0.97;
+  c->pad_value = 0.0; c->pad_to = 0;
+  c->pitch_fmin = 65.40639132514966; c->pitch_fmax = 2093.004522404789;
+  c->pyin_frame_length = 1024; c->pyin_win_length = 0; c->pyin_hop_length = 0; c->n_thresholds = 100;
+  c->beta_a = 2; c->beta_b = 18; c->boltzmann_parameter = 2; c->resolution = 0.1;
+  c->max_transition_rate = 35.92; c->switch_prob = 0.01; c->no_trough_prob = 0.01;
+}
+
+int roar_sup_host_mel_filterbank(const roar_sup_config* cfg, float* out) {
+  std::string v = validate(*cfg);
+  if (!v.empty()) return fail(ROAR_ERR_INVALID_ARG, v);
+  std::vector<float> fb = make_mel_filterbank(*cfg);
+  memcpy(out, fb.data(), fb.size() * sizeof(float));
+  return 0;
+}
+int roar_sup_host_window(const roar_sup_config* cfg, float* out) {
+  std::string v = validate(*cfg);
+  if (!v.empty()) return fail(ROAR_ERR_INVALID_ARG, v);
+  std::vector<float> w = make_window(*cfg);
+  memcpy(out, w.data(), w.size() * sizeof(float));
+  return 0;
+}
+int roar_sup_host_pyin_log_transition(const roar_sup_config* cfg, double* out, int64_t n) {
+  std::string v = validate(*cfg);
+  if (!v.empty()) return fail(ROAR_ERR_INVALID_ARG, v);
+  Geometry g = geometry(*cfg);
+  if (n != (int64_t)4 * g.npb * g.npb) return fail(ROAR_ERR_INVALID_ARG, "log-transition buffer must hold (2*npb)^2 doubles");
+  PyinTables t = make_pyin_tables(*cfg, g);
+  dense_log_transition(t, g, out);
+  return 0;
+}
+int roar_sup_host_pyin_beta_probs(const roar_sup_config* cfg, double* out) {
+  std::string v = validate(*cfg);
+  if (!v.empty()) return fail(ROAR_ERR_INVALID_ARG, v);
+  Geometry g = geometry(*cfg);
+  PyinTables t = make_pyin_tables(*cfg, g);
+  memcpy(out, t.beta_probs.data(), t.beta_probs.size() * sizeof(double));
+  return 0;
+}
+
+int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** out) {
+  if (!cfg || !out) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  std::string v = validate(*cfg);
+  if (!v.empty()) return fail(ROAR_ERR_INVALID_ARG, v);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(ROAR_ERR_NO_DEVICE, "no CUDA device: libroar_sup has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(ROAR_ERR_INVALID_ARG, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(ROAR_ERR_UNSUPPORTED, "libroar_sup is built for sm_100a (Blackwell) only");
+  roar_sup_handle* h = new roar_sup_handle();
+  h->cfg = *cfg; h->g = geometry(*cfg); h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem = prop.sharedMemPerBlockOptin;
+  const Geometry& g = h->g;
+  if (g.pf < 256) { delete h; return fail(ROAR_ERR_UNSUPPORTED, "pyin_frame_length < 256 is not supported"); }
+  if (g.npb > 1024 || g.npb < 2 * g.hw + 2) { delete h; return fail(ROAR_ERR_UNSUPPORTED, "pitch-bin count out of range"); }
+  if (g.min_period < 1 || g.n_lags < 3 || g.max_period >= g.pf - g.pw) { delete h; return fail(ROAR_ERR_INVALID_ARG, "pyin period range empty"); }
+  const char* env_tma = getenv("ROAR_SUP_NO_TMA");
+  h->use_tma = (env_tma && env_tma[0] == '1') ? 0 : 1;
+  int rc = 0;
+#define UP(vec, field) if ((rc = upload(h, vec, &h->field)) != 0) { roar_sup_destroy(h); return rc; }
+  // ---- K1 tables
+  {
+    std::vector<float> win = make_window(*cfg);
+    std::vector<float> fb = make_mel_filterbank(*cfg);
+    MelRows mr = make_mel_rows(fb, g.n_mels, g.n_bins);
+    std::vector<cf32> tw = make_twiddles<cf32, float>(g.M, g.M);
+    std::vector<cf32> twp = make_twiddles<cf32, float>(g.n_fft, g.M + 1);
+    UP(win, d_window) UP(tw, d_tw) UP(twp, d_tw_post)
+    UP(mr.start, d_mel_start) UP(mr.count, d_mel_count) UP(mr.offset, d_mel_offset) UP(mr.weights, d_mel_w)
+    h->mel_nw = (int)mr.weights.size();
+    h->stft_P = g.M / 8 < 1 ? 1 : g.M / 8;
+    h->stft_G = 256 / h->stft_P < 1 ? 1 : 256 / h->stft_P;
+    h->stft_FT = g.n_fft <= 1024 ? 16 : 8;
+    if (h->stft_FT < h->stft_G) h->stft_FT = h->stft_G;
+    h->stft_span = (h->stft_FT - 1) * g.hop + g.n_fft;
+    StftParams sp = stft_params_base(h);
+    h->stft_smem = stft_smem_carve(sp, 256, nullptr, nullptr);
+    if (h->stft_smem > h->max_smem) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "STFT tile does not fit in shared memory"); }
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
+  }
+  // ---- K2 / K3 tables
+  {
+    PyinTables t = make_pyin_tables(*cfg, g);
+    std::vector<cf64> tw = make_twiddles<cf64, double>(g.pf, g.pf);
+    UP(tw, d_tw64) UP(t.thresholds, d_thr) UP(t.beta_probs, d_beta) UP(t.beta_cum, d_beta_cum)
+    UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(t.lt_rows, d_lt_rows) UP(t.row_id, d_row_id)
+    UP(t.freqs, d_freqs)
+    h->n_rows = t.n_rows; h->lt0 = t.lt0; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
+    h->pyin_P = g.pf / 8;
+    h->pyin_G = 256 / h->pyin_P < 1 ? 1 : 256 / h->pyin_P;
+    h->pyin_FT = g.pf <= 1024 ? 16 : 8;
+    if (h->pyin_FT < h->pyin_G) h->pyin_FT = h->pyin_G;
+    h->pyin_span = (h->pyin_FT - 1) * g.ph + g.pf;
+    PyinParams pp = pyin_params_base(h);
+    h->cmnd_smem = cmnd_smem_carve(pp, nullptr, nullptr);
+    h->prob_smem = prob_smem_carve(pp, nullptr, nullptr) * 8 + sizeof(double) * (g.n_thr + 2);
+    if (h->cmnd_smem > h->max_smem || h->prob_smem > h->max_smem) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "pYIN tile does not fit in shared memory"); }
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_cmnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cmnd_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->prob_smem));
+    h->vit_threads = (g.npb + 31) / 32 * 32;
+    if (h->vit_threads < g.kmax) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "kmax exceeds Viterbi block size"); }
+    size_t base = sizeof(cf64) * 2 * g.npb + sizeof(double) * 2 * g.npb + sizeof(double) * 32 + sizeof(int) * 32 +
+                  ((sizeof(uint16_t) * g.npb + 15) & ~(size_t)15) + 128;
+    size_t ltb = sizeof(double) * 2 * (size_t)t.n_rows * g.tw;
+    h->lt_in_smem = base + ltb <= h->max_smem ? 1 : 0;
+    h->vit_smem = base + (h->lt_in_smem ? ltb : 0);
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<true, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<false, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
+  }
+  // ---- K4 log-factorial table
+  {
+    h->lf_n = 1 << 16;
+    std::vector<double> lf(h->lf_n);
+    for (int i = 0; i < h->lf_n; ++i) lf[i] = std::lgamma((double)i + 1.0);
+    UP(lf, d_lf)
+  }
+#undef UP
+  *out = h;
+  return 0;
+}
+
+int roar_sup_set_profiling(roar_sup_handle* h, int on) {
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
+  h->profiling = on ? 1 : 0;
+  return 0;
+}
+int roar_sup_profile_read(roar_sup_handle* h, double* ms_out, int64_t* count_out, int reset) {
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
+  for (auto& pe : h->pending) {
+    cudaEventSynchronize(pe.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) { h->prof_ms[pe.id] += ms; h->prof_n[pe.id] += 1; }
+    h->pool.push_back(pe.a); h->pool.push_back(pe.b);
+  }
+  h->pending.clear();
+  for (int i = 0; i < ROAR_K_COUNT; ++i) {
+    if (ms_out) ms_out[i] = h->prof_ms[i];
+    if (count_out) count_out[i] = h->prof_n[i];
+    if (reset) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  }
+  return 0;
+}
+
+void roar_sup_destroy(roar_sup_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& pe : h->pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+  for (auto e : h->pool) cudaEventDestroy(e);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+int64_t roar_sup_num_frames(const roar_sup_handle* h, int64_t L) {
+  if (h->cfg.exact_pad) {
+    const int64_t p = (h->g.n_fft - h->g.hop) / 2;
+    return (L + 2 * p - h->g.n_fft) / h->g.hop + 1;
+  }
+  return 1 + L / h->g.hop;
+}
+int64_t roar_sup_pyin_num_frames(const roar_sup_handle* h, int64_t L) { return 1 + L / h->g.ph; }
+
+int roar_sup_pyin_geometry(const roar_sup_handle* h, int32_t out8[8]) {
+  const Geometry& g = h->g;
+  out8[0] = g.min_period; out8[1] = g.max_period; out8[2] = g.npb; out8[3] = g.tw;
+  out8[4] = g.ph; out8[5] = g.pw; out8[6] = g.kmax; out8[7] = h->n_rows;
+  return 0;
+}
+
+static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct PyinWs {
+  int32_t *tile_off, *order, *hist, *last_state, *n_cand;
+  double *big, *cand_lp, *lp_unv;
+  uint16_t* cand_bin;
+  size_t total;
+};
+static PyinWs pyin_ws_layout(const roar_sup_handle* h, int32_t n_utts, int64_t frames, int32_t max_T, unsigned char* base) {
+  const Geometry& g = h->g;
+  PyinWs w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { unsigned char* p = base ? base + o : nullptr; o += a256(bytes); return p; };
+  w.tile_off = (int32_t*)take(sizeof(int32_t) * (n_utts + 1));
+  w.order = (int32_t*)take(sizeof(int32_t) * (n_utts + 1));
+  w.hist = (int32_t*)take(sizeof(int32_t) * ((size_t)max_T + 2));
+  w.last_state = (int32_t*)take(sizeof(int32_t) * (n_utts + 1));
+  w.n_cand = (int32_t*)take(sizeof(int32_t) * (frames + 1));
+  w.lp_unv = (double*)take(sizeof(double) * (frames + 1));
+  w.cand_lp = (double*)take(sizeof(double) * (size_t)frames * g.kmax);
+  w.cand_bin = (uint16_t*)take(sizeof(uint16_t) * (size_t)frames * g.kmax);
+  size_t a = sizeof(double) * (size_t)frames * g.n_lags, b = sizeof(uint16_t) * (size_t)frames * 2 * g.npb;
+  w.big = (double*)take(a > b ? a : b);
+  w.total = o;
+  return w;
+}
+
+size_t roar_sup_workspace_bytes(const roar_sup_handle* h, int32_t n_utts, int64_t total_samples,
+                                int64_t total_pyin_frames) {
+  (void)total_samples;
+  // max_T is bounded by the frame total; the histogram is sized for the worst case
+  int64_t max_T = total_pyin_frames < (1 << 20) ? total_pyin_frames : (1 << 20);
+  PyinWs w = pyin_ws_layout(h, n_utts, total_pyin_frames, (int32_t)max_T, nullptr);
+  return w.total + 256;
+}
+
+int roar_sup_logmel_energy(roar_sup_handle* h, const float* d_audio, const int64_t* d_sample_off,
+                           const int32_t* d_sample_len, int32_t n_utts, const int64_t* d_frame_off,
+                           int64_t total_frames, float* d_logmel, float* d_energy, void* d_ws,
+                           size_t ws_bytes, void* stream) {
+  if (!h || !d_audio || !d_sample_off || !d_sample_len || !d_frame_off) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (n_utts <= 0 || total_frames <= 0) return 0;
+  if (ws_bytes < a256(sizeof(int32_t) * (size_t)(n_utts + 1)) || !d_ws) return fail(ROAR_ERR_WORKSPACE, "workspace too small for roar_sup_logmel_energy");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* tile_off = (int32_t*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255);
+  StftParams p = stft_params_base(h);
+  p.audio = d_audio; p.sample_off = d_sample_off; p.sample_len = d_sample_len; p.frame_off = d_frame_off;
+  p.tile_off = tile_off; p.n_utts = n_utts; p.logmel = d_logmel; p.energy = d_energy;
+  LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, p.FT, tile_off));
+  const int64_t max_tiles = total_frames / p.FT + n_utts;
+  LAUNCH(h, ROAR_K_STFT_MEL, st, k_stft_mel<<<(unsigned)max_tiles, 256, h->stft_smem, st>>>(p));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sample_off,
+                  const int32_t* d_sample_len, int32_t n_utts, const int64_t* d_frame_off,
+                  int64_t total_frames, int32_t max_T, float* d_f0, float* d_vflag, float* d_vprob,
+                  void* d_ws, size_t ws_bytes, void* stream) {
+  if (!h || !d_audio || !d_sample_off || !d_sample_len || !d_frame_off || !d_f0 || !d_vflag || !d_vprob)
+    return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (n_utts <= 0 || total_frames <= 0) return 0;
+  if (max_T <= 0 || max_T > (1 << 20)) return fail(ROAR_ERR_INVALID_ARG, "max_frames_per_utt out of range");
+  const Geometry& g = h->g;
+  unsigned char* base = (unsigned char*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255);
+  PyinWs w = pyin_ws_layout(h, n_utts, total_frames, max_T, base);
+  if (!d_ws || w.total + 256 > ws_bytes) return fail(ROAR_ERR_WORKSPACE, "workspace too small for roar_sup_pyin");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  PyinParams p = pyin_params_base(h);
+  p.audio = d_audio; p.sample_off = d_sample_off; p.sample_len = d_sample_len; p.frame_off = d_frame_off;
+  p.tile_off = w.tile_off; p.n_utts = n_utts; p.cmnd = w.big; p.cand_bin = w.cand_bin; p.cand_lp = w.cand_lp;
+  p.n_cand = w.n_cand; p.lp_unvoiced = w.lp_unv; p.voiced_prob = d_vprob; p.total_frames = total_frames;
+  LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, p.FT, w.tile_off));
+  const int64_t max_tiles = total_frames / p.FT + n_utts;
+  LAUNCH(h, ROAR_K_PYIN_CMND, st, k_pyin_cmnd<<<(unsigned)max_tiles, 256, h->cmnd_smem, st>>>(p));
+  int64_t pb = (total_frames + 7) / 8;
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  if (pb > cap) pb = cap;
+  LAUNCH(h, ROAR_K_PYIN_PROBS, st, k_pyin_probs<<<(unsigned)pb, 256, h->prob_smem, st>>>(p));
+
+  // utterances longest-first
+  CUDA_TRY(cudaMemsetAsync(w.hist, 0, sizeof(int32_t) * ((size_t)max_T + 2), st));
+  const int nb = (n_utts + 255) / 256;
+  LAUNCH(h, ROAR_K_LEN_SORT, st, k_len_hist<<<nb, 256, 0, st>>>(d_frame_off, n_utts, max_T, w.hist));
+  LAUNCH(h, ROAR_K_LEN_SORT, st, k_len_scan<<<1, 1024, 0, st>>>(w.hist, max_T + 1));
+  LAUNCH(h, ROAR_K_LEN_SORT, st, k_len_scatter<<<nb, 256, 0, st>>>(d_frame_off, n_utts, max_T, w.hist, w.order));
+
+  VitParams v;
+  memset(&v, 0, sizeof(v));
+  v.frame_off = d_frame_off; v.order = w.order; v.n_utts = n_utts;
+  v.npb = g.npb; v.tw = g.tw; v.hw = g.hw; v.kmax = g.kmax; v.n_rows = h->n_rows;
+  v.lt_rows = h->d_lt_rows; v.row_id = h->d_row_id; v.lt0 = h->lt0; v.li_voiced = h->li_v; v.li_unvoiced = h->li_u;
+  v.cand_bin = w.cand_bin; v.cand_lp = w.cand_lp; v.n_cand = w.n_cand; v.lp_unvoiced = w.lp_unv;
+  v.ptr = (uint16_t*)w.big; v.last_state = w.last_state; v.freqs = h->d_freqs; v.f0 = d_f0; v.voiced_flag = d_vflag;
+  v.lt_in_smem = h->lt_in_smem;
+  if (h->vit_threads <= 640) {
+    if (h->lt_in_smem) LAUNCH(h, ROAR_K_VITERBI, st, (k_pyin_viterbi<true, 640><<<n_utts, h->vit_threads, h->vit_smem, st>>>(v)));
+    else LAUNCH(h, ROAR_K_VITERBI, st, (k_pyin_viterbi<false, 640><<<n_utts, h->vit_threads, h->vit_smem, st>>>(v)));
+  } else {
+    if (h->lt_in_smem) LAUNCH(h, ROAR_K_VITERBI, st, (k_pyin_viterbi<true, 1024><<<n_utts, h->vit_threads, h->vit_smem, st>>>(v)));
+    else LAUNCH(h, ROAR_K_VITERBI, st, (k_pyin_viterbi<false, 1024><<<n_utts, h->vit_threads, h->vit_smem, st>>>(v)));
+  }
+  LAUNCH(h, ROAR_K_BACKTRACK, st, k_pyin_backtrack<<<(n_utts + 127) / 128, 128, 0, st>>>(v));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int roar_sup_align_prior(roar_sup_handle* h, const int32_t* d_text_len, const int32_t* d_mel_len,
+                         int32_t n_utts, const int64_t* d_out_off, int32_t max_mel_len,
+                         double scaling_factor, float* d_prior, void* stream) {
+  if (!h || !d_text_len || !d_mel_len || !d_out_off || !d_prior) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (n_utts <= 0 || max_mel_len <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  PriorParams p;
+  p.text_len = d_text_len; p.mel_len = d_mel_len; p.out_off = d_out_off; p.out = d_prior;
+  p.lf = h->d_lf; p.lf_n = h->lf_n; p.rows_per_cta = 64; p.scaling = scaling_factor;
+  const unsigned gx = (max_mel_len + p.rows_per_cta - 1) / p.rows_per_cta;
+  for (int32_t u0 = 0; u0 < n_utts; u0 += 65535) {
+    p.utt_base = u0;
+    const unsigned gy = n_utts - u0 < 65535 ? n_utts - u0 : 65535;
+    LAUNCH(h, ROAR_K_PRIOR, st, k_align_prior<<<dim3(gx, gy), 256, 0, st>>>(p));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int roar_sup_pitch_partials_init(roar_sup_handle* h, double* d_out, int32_t n_groups, void* stream) {
+  if (!h || !d_out || n_groups <= 0) return fail(ROAR_ERR_INVALID_ARG, "bad argument");
+  k_stats_init<<<(n_groups + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_out, n_groups);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int roar_sup_pitch_partials(roar_sup_handle* h, const float* d_f0, int64_t n, double* d_out5, void* stream) {
+  if (!h || !d_f0 || !d_out5) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (n <= 0) return 0;
+  int64_t nb = (n + 256 * 8 - 1) / (256 * 8);
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (nb > cap) nb = cap;
+  LAUNCH(h, ROAR_K_STATS, (cudaStream_t)stream, k_pitch_partials<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(d_f0, n, d_out5));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int roar_sup_pitch_partials_grouped(roar_sup_handle* h, const float* d_f0, const int64_t* d_frame_off,
+                                    const int32_t* d_group, int32_t n_utts, int32_t n_groups, double* d_out,
+                                    void* stream) {
+  if (!h || !d_f0 || !d_frame_off || !d_group || !d_out) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (n_utts <= 0) return 0;
+  const int64_t threads = (int64_t)n_utts * 32;
+  k_pitch_partials_grouped<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_f0, d_frame_off, d_group, n_utts, n_groups, d_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int64_t roar_fbank_out_frames(const roar_sup_handle* h, int64_t Lmax) {
+  int64_t T = roar_sup_num_frames(h, Lmax);
+  const int pt = h->cfg.pad_to;
+  if (pt > 0 && T % pt != 0) T += pt - T % pt;
+  return T;
+}
+
+__global__ void k_fbank_setup(const int64_t* len, int32_t B, int64_t Lmax, int64_t T_full, int32_t n_fft,
+                              int32_t hop, int32_t pad_amount, int64_t* sample_off, int32_t* sample_len,
+                              int64_t* frame_off, int64_t* out_len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    sample_off[i] = (int64_t)i * Lmax;
+    sample_len[i] = (int32_t)Lmax;
+    int64_t num = len[i] + pad_amount - n_fft;
+    int64_t q = num >= 0 ? num / hop : -((-num + hop - 1) / hop);   // floor division
+    out_len[i] = q + 1;
+  }
+  if (i <= B) frame_off[i] = (int64_t)i * T_full;
+}
+
+int roar_fbank_forward(roar_sup_handle* h, const float* d_x, const int64_t* d_len, int32_t B, int64_t Lmax,
+                       float* d_out, int64_t* d_out_len, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!h || !d_x || !d_len || !d_out || !d_out_len) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (B <= 0) return 0;
+  const Geometry& g = h->g;
+  const int64_t pad = h->cfg.exact_pad ? (g.n_fft - g.hop) / 2 : g.n_fft / 2;
+  if (Lmax <= pad) return fail(ROAR_ERR_INVALID_ARG, "input shorter than the reflect padding");
+  const int64_t T_full = roar_sup_num_frames(h, Lmax), Tpad = roar_fbank_out_frames(h, Lmax);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* base = (unsigned char*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { unsigned char* p = base + o; o += a256(bytes); return p; };
+  int64_t* sample_off = (int64_t*)take(sizeof(int64_t) * (B + 1));
+  int32_t* sample_len = (int32_t*)take(sizeof(int32_t) * (B + 1));
+  int64_t* frame_off = (int64_t*)take(sizeof(int64_t) * (B + 1));
+  int32_t* tile_off = (int32_t*)take(sizeof(int32_t) * (B + 1));
+  if (!d_ws || o + 256 > ws_bytes) return fail(ROAR_ERR_WORKSPACE, "workspace too small for roar_fbank_forward");
+  k_fbank_setup<<<(B + 256) / 256, 256, 0, st>>>(d_len, B, Lmax, T_full, g.n_fft, g.hop, (int32_t)(2 * pad),
+                                                 sample_off, sample_len, frame_off, d_out_len);
+  StftParams p = stft_params_base(h);
+  p.audio = d_x; p.sample_off = sample_off; p.sample_len = sample_len; p.frame_off = frame_off;
+  p.tile_off = tile_off; p.n_utts = B; p.logmel = d_out; p.energy = nullptr;
+  p.out_utt_stride = (int64_t)g.n_mels * Tpad; p.out_row_stride = Tpad;
+  LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(frame_off, B, p.FT, tile_off));
+  const int64_t max_tiles = (T_full * B) / p.FT + B;
+  LAUNCH(h, ROAR_K_STFT_MEL, st, k_stft_mel<<<(unsigned)max_tiles, 256, h->stft_smem, st>>>(p));
+  NormParams np;
+  np.x = d_out; np.seq_len = d_out_len; np.B = B; np.n_mels = g.n_mels; np.T_full = (int32_t)T_full;
+  np.Tpad = (int32_t)Tpad; np.mode = h->cfg.normalize; np.pad_value = (float)h->cfg.pad_value;
+  dim3 grid(np.mode == ROAR_NORM_ALL_FEATURES ? 1 : g.n_mels, B);
+  LAUNCH(h, ROAR_K_FBANK_NORM, st, k_fbank_normalize<<<grid, 256, 0, st>>>(np));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+"""TEST INFRASTRUCTURE ONLY: CPU emulation of the CUDA kernels' per-thread code (see hostemu.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(HERE, "libhostemu.so")
+        src = os.path.join(HERE, "hostemu.cpp")
+        deps = [src] + [os.path.join(HERE, "..", "..", "roar_b200", "csrc", f)
+                        for f in os.listdir(os.path.join(HERE, "..", "..", "roar_b200", "csrc"))]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+        _LIB = ctypes.CDLL(so)
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def logmel_energy(cfg, audio):
+    c = cfg.to_c()
+    audio = _f32(audio)
+    L = len(audio)
+    p = (cfg.n_fft - cfg.hop) // 2 if cfg.exact_pad else cfg.n_fft // 2
+    T = (L + 2 * p - cfg.n_fft) // cfg.hop + 1
+    lm = np.zeros((cfg.n_mels, T), dtype=np.float32)
+    en = np.zeros(T, dtype=np.float32)
+    rc = lib().emu_logmel_energy(ctypes.byref(c), audio.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(L),
+                                 lm.ctypes.data_as(ctypes.c_void_p), en.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return lm, en
+
+
+def pyin(cfg, audio, n_lags):
+    c = cfg.to_c()
+    audio = _f32(audio)
+    L = len(audio)
+    T = 1 + L // cfg.pyin_hop
+    f0 = np.zeros(T, np.float32)
+    vf = np.zeros(T, np.float32)
+    vp = np.zeros(T, np.float32)
+    cm = np.zeros((T, n_lags), np.float64)
+    st = np.zeros(T, np.int32)
+    rc = lib().emu_pyin(ctypes.byref(c), audio.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(L),
+                        f0.ctypes.data_as(ctypes.c_void_p), vf.ctypes.data_as(ctypes.c_void_p),
+                        vp.ctypes.data_as(ctypes.c_void_p), cm.ctypes.data_as(ctypes.c_void_p),
+                        st.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return f0, vf, vp, cm, st
+
+
+def prior(N, M, scaling=1.0):
+    out = np.zeros((M, N), np.float32)
+    rc = lib().emu_prior(ctypes.c_int32(N), ctypes.c_int32(M), ctypes.c_double(scaling),
+                         out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return out

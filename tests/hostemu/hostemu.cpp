@@ -1,0 +1,243 @@
+// TEST INFRASTRUCTURE ONLY -- never loaded by the product (roar_b200/).
+//
+// Runs the per-thread code of the CUDA kernels (the HD functions of roar_b200/csrc/*.cuh, the same
+// source the GPU compiles) on the CPU: the grid becomes loops over tiles, each __syncthreads()
+// phase becomes a loop over thread ids.  Lets `pytest -m "not gpu"` check kernel logic against the
+// oracle in a container without a GPU.  Device-only parts (TMA staging, warp shuffles) are
+// replaced by their plain equivalents here and are covered by the `-m gpu` tests.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../roar_b200/csrc/common.cuh"
+#include "../../roar_b200/csrc/fft.cuh"
+#include "../../roar_b200/csrc/tables.hpp"
+#include "../../roar_b200/csrc/k_stft_mel.cuh"
+#include "../../roar_b200/csrc/k_pyin_front.cuh"
+#include "../../roar_b200/csrc/k_viterbi.cuh"
+#include "../../roar_b200/csrc/k_misc.cuh"
+
+using namespace roar;
+
+extern "C" {
+
+// ---------------------------------------------------------------------------- K1
+int emu_logmel_energy(const roar_sup_config* cfg, const float* audio, int64_t L, float* logmel, float* energy) {
+  if (!validate(*cfg).empty()) return -1;
+  Geometry g = geometry(*cfg);
+  std::vector<float> win = make_window(*cfg);
+  std::vector<float> fb = make_mel_filterbank(*cfg);
+  MelRows mr = make_mel_rows(fb, g.n_mels, g.n_bins);
+  std::vector<cf32> tw = make_twiddles<cf32, float>(g.M, g.M);
+  std::vector<cf32> twp = make_twiddles<cf32, float>(g.n_fft, g.M + 1);
+  const int NT = 256;
+  StftParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_fft = g.n_fft; p.hop = g.hop; p.M = g.M; p.n_bins = g.n_bins; p.n_mels = g.n_mels;
+  p.P = g.M / 8; p.G = NT / p.P < 1 ? 1 : NT / p.P;
+  p.FT = g.n_fft <= 1024 ? 16 : 8; if (p.FT < p.G) p.FT = p.G;
+  p.span = (p.FT - 1) * g.hop + g.n_fft;
+  p.pad_left = cfg->exact_pad ? (g.n_fft - g.hop) / 2 : g.n_fft / 2;
+  p.floor_ = (float)cfg->spec_floor; p.mag_power = (float)cfg->mag_power; p.log_guard = (float)cfg->log_guard;
+  p.preemph = (float)cfg->preemph; p.log_mode = cfg->log_mode; p.has_preemph = cfg->has_preemph;
+  p.window = win.data(); p.tw = tw.data(); p.tw_post = twp.data();
+  p.mel_start = mr.start.data(); p.mel_count = mr.count.data(); p.mel_offset = mr.offset.data();
+  p.mel_w = mr.weights.data(); p.mel_nw = (int)mr.weights.size();
+  int64_t T = cfg->exact_pad ? (L + 2 * p.pad_left - g.n_fft) / g.hop + 1 : 1 + L / g.hop;
+  int64_t sample_off[1] = {0}; int32_t sample_len[1] = {(int32_t)L};
+  int64_t frame_off[2] = {0, T};
+  int32_t n_tiles = (int32_t)((T + p.FT - 1) / p.FT);
+  int32_t tile_off[2] = {0, n_tiles};
+  p.audio = audio; p.sample_off = sample_off; p.sample_len = sample_len; p.frame_off = frame_off;
+  p.tile_off = tile_off; p.n_utts = 1; p.logmel = logmel; p.energy = energy;
+  std::vector<unsigned char> smem(stft_smem_carve(p, NT, nullptr, nullptr) + 64);
+  for (int tile = 0; tile < n_tiles + 1; ++tile) {
+    StftSmem s;
+    stft_smem_carve(p, NT, smem.data(), &s);
+    StftTile t;
+    if (!stft_locate(p, tile, &t)) continue;
+    const int hi = (t.nf - 1) * p.hop + p.n_fft;
+    for (int tid = 0; tid < NT; ++tid) { stft_phase_tables(p, s, tid, NT); stft_phase_audio(p, t, s, tid, NT, 0, hi); }
+    const int n_groups = (t.nf + p.G - 1) / p.G;
+    for (int gi = 0; gi < n_groups; ++gi) {
+      for (int tid = 0; tid < NT; ++tid) stft_first_pass<8>(p, t, s, gi, tid);
+      const FftPlan plan = make_plan(p.M);
+      int Ns = plan.radix[0];
+      const cf32* src = s.bufA; cf32* dst = s.bufB;
+      for (int ps = 1; ps < plan.n_pass; ++ps) {
+        for (int tid = 0; tid < NT; ++tid) stft_pass_any(plan.radix[ps], p, t, s, gi, tid, Ns, src, dst);
+        Ns *= plan.radix[ps];
+        const cf32* tmp = src; src = dst; dst = const_cast<cf32*>(tmp);
+      }
+      float* spec = (float*)dst;
+      for (int tid = 0; tid < NT; ++tid) stft_phase_post(p, t, s, gi, tid, src, spec);
+      for (int tid = 0; tid < NT; ++tid) stft_phase_mel(p, t, s, gi, tid, NT, spec);
+    }
+    for (int tid = 0; tid < NT; ++tid) stft_phase_store(p, t, s, tid, NT);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- K2 + K3
+// stage outputs (any may be null): cmnd [T, n_lags]; states [T]
+int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f0, float* vflag, float* vprob,
+             double* cmnd_out, int32_t* states_out) {
+  if (!validate(*cfg).empty()) return -1;
+  Geometry g = geometry(*cfg);
+  PyinTables tb = make_pyin_tables(*cfg, g);
+  std::vector<cf64> tw = make_twiddles<cf64, double>(g.pf, g.pf);
+  const int NT = 256;
+  PyinParams p;
+  memset(&p, 0, sizeof(p));
+  p.F = g.pf; p.W = g.pw; p.hop = g.ph; p.H = g.pf / 2;
+  p.min_period = g.min_period; p.max_period = g.max_period; p.n_lags = g.n_lags;
+  p.P = g.pf / 8; p.G = NT / p.P < 1 ? 1 : NT / p.P;
+  p.FT = g.pf <= 1024 ? 16 : 8; if (p.FT < p.G) p.FT = p.G;
+  p.span = (p.FT - 1) * g.ph + g.pf;
+  p.npb = g.npb; p.nbps = g.nbps; p.kmax = g.kmax; p.n_thr = g.n_thr;
+  p.sr = cfg->sample_rate; p.fmin = cfg->pitch_fmin; p.no_trough_prob = cfg->no_trough_prob;
+  p.tw = tw.data(); p.thresholds = tb.thresholds.data(); p.beta_probs = tb.beta_probs.data();
+  p.beta_cum = tb.beta_cum.data(); p.boltz_exp = tb.boltz_exp.data(); p.boltz_fact = tb.boltz_fact.data();
+  const int64_t T = 1 + L / g.ph;
+  int64_t sample_off[1] = {0}; int32_t sample_len[1] = {(int32_t)L};
+  int64_t frame_off[2] = {0, T};
+  int32_t n_tiles = (int32_t)((T + p.FT - 1) / p.FT);
+  int32_t tile_off[2] = {0, n_tiles};
+  std::vector<double> cmnd((size_t)T * g.n_lags), cand_lp((size_t)T * g.kmax), lp_unv(T);
+  std::vector<uint16_t> cand_bin((size_t)T * g.kmax);
+  std::vector<int32_t> n_cand(T);
+  p.audio = audio; p.sample_off = sample_off; p.sample_len = sample_len; p.frame_off = frame_off;
+  p.tile_off = tile_off; p.n_utts = 1; p.cmnd = cmnd.data(); p.cand_bin = cand_bin.data();
+  p.cand_lp = cand_lp.data(); p.n_cand = n_cand.data(); p.lp_unvoiced = lp_unv.data(); p.voiced_prob = vprob;
+  p.total_frames = T;
+  // ---- K2a
+  std::vector<unsigned char> smem(cmnd_smem_carve(p, nullptr, nullptr) + 64);
+  std::vector<cf64> regs((size_t)NT * 8);
+  const FftPlan planF = make_plan(p.F), planH = make_plan(p.H);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    CmndSmem s;
+    cmnd_smem_carve(p, smem.data(), &s);
+    PyinTile t;
+    if (!pyin_locate(p, tile, &t)) continue;
+    for (int tid = 0; tid < NT; ++tid) cmnd_phase_load(p, t, s, tid, NT);
+    for (int tid = 0; tid < NT; ++tid) cmnd_phase_energy(p, t, s, tid, NT);
+    const int n_groups = (t.nf + p.G - 1) / p.G;
+    for (int gi = 0; gi < n_groups; ++gi) {
+      for (int tid = 0; tid < NT; ++tid) cmnd_first_pass(p, t, s, gi, tid);
+      int Ns = 8;
+      for (int ps = 1; ps < planF.n_pass; ++ps) {
+        const int R = planF.radix[ps];
+        for (int tid = 0; tid < NT; ++tid) {
+          cf64* r = regs.data() + (size_t)tid * 8;
+          if (R == 8) cmnd_pass_compute<8, false>(p, t, s, gi, tid, p.F, Ns, 1, s.buf, p.F, r);
+          else if (R == 4) cmnd_pass_compute<4, false>(p, t, s, gi, tid, p.F, Ns, 1, s.buf, p.F, r);
+          else cmnd_pass_compute<2, false>(p, t, s, gi, tid, p.F, Ns, 1, s.buf, p.F, r);
+        }
+        for (int tid = 0; tid < NT; ++tid) {
+          const cf64* r = regs.data() + (size_t)tid * 8;
+          if (R == 8) cmnd_pass_store<8>(p, t, gi, tid, p.F, Ns, s.buf, p.F, r);
+          else if (R == 4) cmnd_pass_store<4>(p, t, gi, tid, p.F, Ns, s.buf, p.F, r);
+          else cmnd_pass_store<2>(p, t, gi, tid, p.F, Ns, s.buf, p.F, r);
+        }
+        Ns *= R;
+      }
+      for (int tid = 0; tid < NT; ++tid) cmnd_phase_product(p, t, s, gi, tid);
+      for (int tid = 0; tid < NT; ++tid) cmnd_phase_pack_inverse(p, t, s, gi, tid);
+      Ns = 1;
+      for (int ps = 0; ps < planH.n_pass; ++ps) {
+        const int R = planH.radix[ps];
+        for (int tid = 0; tid < NT; ++tid) {
+          cf64* r = regs.data() + (size_t)tid * 8;
+          if (R == 8) cmnd_pass_compute<8, true>(p, t, s, gi, tid, p.H, Ns, 2, s.buf, p.F, r);
+          else if (R == 4) cmnd_pass_compute<4, true>(p, t, s, gi, tid, p.H, Ns, 2, s.buf, p.F, r);
+          else cmnd_pass_compute<2, true>(p, t, s, gi, tid, p.H, Ns, 2, s.buf, p.F, r);
+        }
+        for (int tid = 0; tid < NT; ++tid) {
+          const cf64* r = regs.data() + (size_t)tid * 8;
+          if (R == 8) cmnd_pass_store<8>(p, t, gi, tid, p.H, Ns, s.buf, p.F, r);
+          else if (R == 4) cmnd_pass_store<4>(p, t, gi, tid, p.H, Ns, s.buf, p.F, r);
+          else cmnd_pass_store<2>(p, t, gi, tid, p.H, Ns, s.buf, p.F, r);
+        }
+        Ns *= R;
+      }
+      for (int tid = 0; tid < NT; ++tid) cmnd_phase_diff(p, t, s, gi, tid, s.buf);
+      for (int tid = 0; tid < NT; ++tid) cmnd_phase_scan1(p, t, s, gi, tid);
+      for (int tid = 0; tid < NT; ++tid) cmnd_phase_scan2(p, t, s, gi, tid, s.chunk + (size_t)p.G * 32);
+      for (int tid = 0; tid < NT; ++tid) cmnd_phase_emit(p, t, s, gi, tid, s.chunk + (size_t)p.G * 32);
+    }
+  }
+  if (cmnd_out) memcpy(cmnd_out, cmnd.data(), cmnd.size() * sizeof(double));
+  // ---- K2b
+  {
+    std::vector<unsigned char> sm(prob_smem_carve(p, nullptr, nullptr) + 64);
+    ProbSmem s;
+    prob_smem_carve(p, sm.data(), &s);
+    for (int64_t fr = 0; fr < T; ++fr) {
+      for (int l = 0; l < 32; ++l) prob_phase0(p, s, fr, l);
+      for (int l = 0; l < 32; ++l) prob_phase1(p, s, l);
+      for (int l = 0; l < 32; ++l) prob_phase2(p, s, l);
+      for (int l = 0; l < 32; ++l) prob_phase3(p, s, l, tb.thresholds.data());
+      for (int l = 0; l < 32; ++l) prob_phase4(p, s, l);
+      for (int l = 0; l < 32; ++l) prob_phase5(p, s, l);
+      for (int l = 0; l < 32; ++l) prob_phase6(p, s, fr, l);
+    }
+  }
+  // ---- K3 (same per-bin step function; the block argmax is a plain scan here)
+  VitParams v;
+  memset(&v, 0, sizeof(v));
+  v.npb = g.npb; v.tw = g.tw; v.hw = g.hw; v.kmax = g.kmax; v.n_rows = tb.n_rows;
+  v.lt0 = tb.lt0; v.li_voiced = tb.li_voiced; v.li_unvoiced = tb.li_unvoiced;
+  const int npb = g.npb;
+  std::vector<cf64> V(2 * (size_t)npb);
+  std::vector<double> lpv(npb, tb.lt0);
+  std::vector<uint16_t> ptr((size_t)T * 2 * npb);
+  auto argmax = [&](const cf64* Vc, int* k, double* m) {
+    double best = -1e308; int bk = 0x7fffffff;
+    for (int b = 0; b < 2; ++b)
+      for (int j = 0; j < npb; ++j) {
+        const double val = b ? Vc[j].y : Vc[j].x;
+        if (val > best) { best = val; bk = b * npb + j; }
+      }
+    *k = bk; *m = best;
+  };
+  for (int c = 0; c < n_cand[0]; ++c) lpv[cand_bin[c]] = cand_lp[c];
+  for (int j = 0; j < npb; ++j) { V[j].x = lpv[j] + tb.li_voiced; V[j].y = lp_unv[0] + tb.li_unvoiced; }
+  for (int c = 0; c < n_cand[0]; ++c) lpv[cand_bin[c]] = tb.lt0;
+  for (int64_t t = 1; t < T; ++t) {
+    const cf64* Vc = V.data() + (size_t)((t - 1) & 1) * npb;
+    cf64* Vn = V.data() + (size_t)(t & 1) * npb;
+    int kstar; double vmax;
+    argmax(Vc, &kstar, &vmax);
+    for (int c = 0; c < n_cand[t]; ++c) lpv[cand_bin[(size_t)t * g.kmax + c]] = cand_lp[(size_t)t * g.kmax + c];
+    for (int j = 0; j < npb; ++j)
+      vit_step_bin(v, j, Vc, tb.lt_rows.data(), tb.row_id.data(), lpv[j], lp_unv[t], kstar, vmax, &Vn[j],
+                   ptr.data() + (size_t)t * 2 * npb);
+    for (int c = 0; c < n_cand[t]; ++c) lpv[cand_bin[(size_t)t * g.kmax + c]] = tb.lt0;
+  }
+  int s; double m;
+  argmax(V.data() + (size_t)((T - 1) & 1) * npb, &s, &m);
+  for (int64_t t = T - 1; t >= 0; --t) {
+    const bool voiced = s < npb;
+    if (states_out) states_out[t] = s;
+    f0[t] = voiced ? (float)tb.freqs[s] : 0.f;
+    vflag[t] = voiced ? 1.f : 0.f;
+    if (t > 0) s = ptr[(size_t)t * 2 * npb + s];
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- K4
+int emu_prior(int32_t N, int32_t M, double scaling, float* out) {
+  std::vector<double> lf(4096);
+  for (size_t i = 0; i < lf.size(); ++i) lf[i] = std::lgamma((double)i + 1.0);
+  PriorParams p;
+  memset(&p, 0, sizeof(p));
+  p.lf = lf.data(); p.lf_n = (int)lf.size(); p.scaling = scaling;
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < N; ++k)
+      out[(size_t)m * N + k] = scaling == 1.0 ? prior_value_int(p, N, M, m + 1, k) : prior_value_real(p, N, M, m + 1, k);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+"""The kernels' per-thread code (roar_b200/csrc/*.cuh), executed on the CPU by tests/hostemu, against
+the oracle.  This pins kernel LOGIC without a GPU; the `-m gpu` tests pin the real launches."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import hostemu  # noqa: E402
+from oracle import fbank as ofbank, prior as oprior, pyin as opyin, spec as ospec  # noqa: E402
+from roar_b200 import synth  # noqa: E402
+from roar_b200.config import SupConfig  # noqa: E402
+
+FMIN, FMAX = 65.40639132514966, 2093.004522404789
+
+
+def _wav(i, n, sr=22050, seed=1234):
+    u = synth.corpus_manifest("C1", i + 1)[i]
+    return synth.synth_utterance(seed, u.utt_id, n, sr, u.speaker)
+
+
+@pytest.mark.parametrize("n", [513, 4096, 4097, 30000])
+def test_emu_logmel_energy(n):
+    cfg = SupConfig(highfreq=8000.0)
+    y = _wav(2, n)
+    lm, en = hostemu.logmel_energy(cfg, y)
+    olm, oen = ospec.log_mel_energy(y)
+    assert (np.abs(lm - olm[0]) / np.maximum(1, np.abs(olm[0]))).max() <= 1e-4
+    np.testing.assert_allclose(en, oen, rtol=1e-4)
+
+
+@pytest.mark.parametrize("kw", [dict(sample_rate=44100, n_fft=2048, hop_length=512, highfreq=None),
+                                dict(sample_rate=16000, n_fft=512, win_length=400, hop_length=160, highfreq=None, pyin_frame_length=512),
+                                dict(sample_rate=22050, n_fft=256, hop_length=64, n_mels=40, highfreq=None)])
+def test_emu_logmel_other_geometries(kw):
+    cfg = SupConfig(**kw)
+    y = _wav(1, 20000, sr=kw["sample_rate"])
+    lm, en = hostemu.logmel_energy(cfg, y)
+    olm, oen = ospec.log_mel_energy(y, sr=cfg.sample_rate, n_fft=cfg.n_fft, hop_length=cfg.hop,
+                                    win_length=cfg.win, n_mels=cfg.n_mels, fmin=0.0, fmax=cfg.highfreq)
+    assert lm.shape == olm[0].shape
+    assert (np.abs(lm - olm[0]) / np.maximum(1, np.abs(olm[0]))).max() <= 1e-4
+    np.testing.assert_allclose(en, oen, rtol=1e-4)
+
+
+def test_emu_fbank_front_matches_oracle_pre_normalisation():
+    """FilterbankFeatures front end (pre-emphasis, power spectrum, log add) through the K1 code."""
+    y = _wav(0, 16000, sr=16000, seed=5)
+    cfg = SupConfig(sample_rate=16000, n_fft=512, win_length=400, hop_length=160, highfreq=None, spec_floor=0.0,
+                    mag_power=2.0, log_mode="add", log_guard=2 ** -24, preemph=0.97, pyin_frame_length=512)
+    lm, _ = hostemu.logmel_energy(cfg, y)
+    ref, _ = ofbank.FilterbankFeaturesOracle(sample_rate=16000, n_window_size=400, n_window_stride=160, nfilt=80,
+                                             n_fft=512, normalize=None, pad_to=0).forward(y[None, :], [len(y)])
+    assert (np.abs(lm - ref[0]) / np.maximum(1, np.abs(ref[0]))).max() <= 1e-4
+
+
+@pytest.mark.parametrize("i,n", [(0, 44100), (1, 30000), (2, 9000)])
+def test_emu_pyin_equals_oracle(i, n):
+    cfg = SupConfig(highfreq=8000.0)
+    y = _wav(i, n)
+    f0, vf, vp, cm, st = hostemu.pyin(cfg, y, 329)
+    of0, ovf, ovp, info = opyin.pyin(y, FMIN, FMAX, sr=22050, frame_length=1024, fill_na=0.0, return_internals=True)
+    assert np.abs(cm - info["yin_frames"].T).max() < 1e-9
+    assert np.array_equal(st, info["states"])
+    assert np.array_equal(vf.astype(bool), ovf)
+    assert np.array_equal(f0, of0.astype(np.float32))
+    assert np.abs(vp - ovp).max() < 1e-6
+
+
+def test_emu_pyin_44k_and_edge_inputs():
+    cfg = SupConfig(sample_rate=44100, n_fft=2048, hop_length=512, highfreq=None)
+    y = _wav(1, 40000, sr=44100)
+    f0, vf, vp, cm, st = hostemu.pyin(cfg, y, 655)
+    of0, ovf, ovp, info = opyin.pyin(y, FMIN, FMAX, sr=44100, frame_length=2048, fill_na=0.0, return_internals=True)
+    assert np.array_equal(st, info["states"]) and np.abs(vp - ovp).max() < 1e-6
+    cfg = SupConfig(highfreq=8000.0)
+    for y in (np.zeros(3000, np.float32), np.ones(1, np.float32), _wav(0, 300)):
+        f0, vf, vp, cm, st = hostemu.pyin(cfg, y, 329)
+        of0, ovf, ovp = opyin.pyin(y, FMIN, FMAX, sr=22050, frame_length=1024, fill_na=0.0)
+        assert np.array_equal(vf.astype(bool), ovf) and np.array_equal(f0, of0.astype(np.float32))
+
+
+def test_emu_prior(golden_dir):
+    g = np.load(os.path.join(golden_dir, "prior_ref.npz"))
+    for k in ("p_7_13", "p_100_560", "p_1_4", "p_2_9"):
+        _, n, m = k.split("_")
+        got = hostemu.prior(int(n), int(m))
+        ref64 = oprior.prior_f64(int(n), int(m))
+        assert np.abs(got - ref64).max() < 1e-6
+        assert np.abs(got - g[k]).max() < 2e-3
+    got = hostemu.prior(50, 300, 0.5)
+    assert np.abs(got - oprior.prior_f64(50, 300, 0.5)).max() < 1e-6
