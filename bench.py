@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- sup-data extraction throughput (audio-seconds processed per second) on B200.
+
+A "step" is one pass of the whole hot path (log-mel + energy, pYIN f0 / voiced flag / voiced
+probability, beta-binomial prior, pitch-stat partials [+ one all-reduce when N > 1]) over the
+BASELINE.json config-2 workload: an LJSpeech-shaped 24 h synthetic manifest (13 100 utterances,
+22.05 kHz, n_fft 1024 / hop 256 / 80 mels, 0-8000 Hz, pitch C2-C7).  With N GPUs every rank
+processes its own 24 h shard (weak scaling, no data-path collective; one all-reduce of the five
+pitch-stat partials per step).
+
+  value     audio-s/s with the audio already resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the public host API with the audio in pinned HOST memory: per step the
+            packed audio is copied host->device and every tensor the reference caches on disk
+            (log_mel, pitch, voiced_mask, p_voiced, energy) plus the pitch statistics is copied back
+  roofline  the dominant kernel: its algorithmic HBM bytes / its CUDA-event time vs measured HBM peak
+  cpu_baseline  the reference-style CPU path (oracle port, dense Viterbi, 3 STFTs per utterance) on
+            this box's host cores over a bounded sample of the same manifest (rank 0, N = 1 only)
+
+`--impl reference` times that CPU path alone and prints the same JSON line shape.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KERNEL_NAMES = ["tile_offsets", "stft_mel", "pyin_cmnd", "pyin_probs", "len_sort", "viterbi", "backtrack",
+                "prior", "stats", "fbank_norm"]
+SR, HOP, N_MELS = 22050, 256, 80
+WORKLOAD = "C2: LJSpeech-shaped 24 h synthetic manifest, 22.05 kHz, n_fft 1024/hop 256/80 mels"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, per_step=None):
+    """The reference-style CPU extraction, `steps` timed bounded samples of the config-2 manifest."""
+    from oracle import extract as oextract
+    cores = os.cpu_count() or 1
+    per_step = per_step or cores
+    first = 0
+    for _ in range(warmup):
+        oextract.timed_cpu_extraction("C2", first, min(per_step, cores), cores)
+    audio = wall = 0.0
+    for s in range(steps):
+        a, w, p = oextract.timed_cpu_extraction("C2", first + s * per_step, per_step, cores)
+        audio += a
+        wall += w
+    return audio, wall, cores, per_step
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-utts", type=int, default=13100, help="utterances of the config-2 manifest per rank")
+    ap.add_argument("--chunk-utts", type=int, default=0, help="utterances per device-resident call (0 = all)")
+    ap.add_argument("--e2e-chunk-utts", type=int, default=1640, help="utterances per streamed host chunk")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        audio, wall, cores, per_step = cpu_reference_run(args.steps, min(args.warmup, 1), None)
+        v = audio / wall
+        print(json.dumps({
+            "impl": "reference", "metric": "audio-seconds processed/sec (sup-data extraction)", "value": v,
+            "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"{per_step} utterances per step"},
+            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} x {per_step} utterances of the config-2 manifest, "
+                                       "oracle port of TTSDataset.__getitem__ (3 STFTs, dense-Viterbi pyin, "
+                                       "float32 prior), one process per core"},
+            "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ CPU baseline first (before CUDA init)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = max(8, min(cores, 64))
+        audio, wall, cores, per_step = cpu_reference_run(1, 0, n)
+        cpu_baseline = {"value": audio / wall, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                        "sample": f"first {n} utterances ({audio:.0f} audio-s) of the config-2 manifest, oracle "
+                                  "port of TTSDataset.__getitem__ (3 STFTs, dense-Viterbi pyin, float32 "
+                                  "prior), one process per core"}
+
+    import torch
+    import torch.distributed as dist
+
+    from roar_b200 import synth
+    from roar_b200.config import SupConfig
+    from roar_b200.extractor import SupDataExtractor, finalize_pitch_stats
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ex = SupDataExtractor(SupConfig(highfreq=8000.0), dev)
+    # every rank its own 24 h shard (same manifest shape, different seed)
+    synth.CORPORA["C2_rank"] = dict(synth.CORPORA["C2"], seed=synth.CORPORA["C2"]["seed"] + 1000 * rank)
+    man, audio, offs, lens = synth.synth_corpus_device("C2_rank", dev, n_utts=args.n_utts)
+    offs_h = offs.cpu().numpy()
+    lens_h = lens.cpu().numpy().astype(np.int64)
+    text_lens = np.array([u.text_len for u in man], dtype=np.int32)
+    audio_s = float(lens_h.sum()) / SR
+    n_utts = len(man)
+    chunk = args.chunk_utts or n_utts
+    bounds = [(a, min(a + chunk, n_utts)) for a in range(0, n_utts, chunk)]
+
+    def chunk_batch(a, b):
+        lo = int(offs_h[a])
+        hi = int(offs_h[b - 1] + (lens_h[b - 1] + 3) // 4 * 4)
+        return ex.batch_from_device(audio[lo:hi], offs_h[a:b] - lo, lens_h[a:b])
+
+    batches = [chunk_batch(a, b) for a, b in bounds]
+    stats = ex.new_pitch_partials(1)
+
+    def step_device():
+        ex.lib.roar_sup_pitch_partials_init(ex._h, ctypes.c_void_p(stats.data_ptr()), 1,
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        for (a, b), bt in zip(bounds, batches):
+            out = ex.extract(bt, text_lens=text_lens[a:b], stats=stats)
+            del out
+        if world > 1:
+            red = stats.clone()
+            dist.all_reduce(red[:, :3], op=dist.ReduceOp.SUM)
+            mn, mx = red[:, 3].clone(), red[:, 4].clone()
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            red[:, 3], red[:, 4] = mn, mx
+            return red
+        return stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = ex.kernel_launches
+    ex.lib.roar_sup_set_profiling(ex._h, 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        final = step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    launches = ex.kernel_launches - launches0
+    kms = (ctypes.c_double * 10)()
+    kcnt = (ctypes.c_int64 * 10)()
+    ex.lib.roar_sup_profile_read(ex._h, kms, kcnt, 1)
+    ex.lib.roar_sup_set_profiling(ex._h, 0)
+    pstats = finalize_pitch_stats(final)
+
+    # ------------------------------------------------------------------ e2e: host buffers, copies inside
+    e2e = None
+    if not args.no_e2e:
+        total_samples = int(audio.numel())
+        host_audio = torch.empty(total_samples, dtype=torch.float32, pin_memory=True)
+        host_audio.copy_(audio)
+        frames_all = int((1 + lens_h // HOP).sum())
+        host_out = {k: torch.empty(frames_all * (N_MELS if k == "log_mel" else 1), dtype=torch.float32,
+                                   pin_memory=True)
+                    for k in ("log_mel", "pitch", "voiced_mask", "p_voiced", "energy")}
+        host_stats = torch.empty(1, 5, dtype=torch.float64, pin_memory=True)
+        ec = args.e2e_chunk_utts
+        eb = [(a, min(a + ec, n_utts)) for a in range(0, n_utts, ec)]
+        copy_stream = torch.cuda.Stream(dev)
+        out_stream = torch.cuda.Stream(dev)
+        frame_cum = np.concatenate([[0], np.cumsum(1 + lens_h // HOP)])
+
+        def step_e2e():
+            st = ex.new_pitch_partials(1)
+            main = torch.cuda.current_stream()
+            staged = {}
+
+            def stage(i):
+                a, b = eb[i]
+                lo = int(offs_h[a])
+                hi = int(offs_h[b - 1] + (lens_h[b - 1] + 3) // 4 * 4)
+                with torch.cuda.stream(copy_stream):
+                    d = host_audio[lo:hi].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                staged[i] = (d, ev, lo)
+
+            stage(0)
+            pending = []
+            for i, (a, b) in enumerate(eb):
+                d, ev, lo = staged.pop(i)
+                if i + 1 < len(eb):
+                    stage(i + 1)
+                main.wait_event(ev)
+                bt = ex.batch_from_device(d, offs_h[a:b] - lo, lens_h[a:b])
+                out = ex.extract(bt, text_lens=text_lens[a:b], stats=st)
+                done = torch.cuda.Event()
+                done.record(main)
+                f_lo, f_hi = int(frame_cum[a]), int(frame_cum[b])
+                with torch.cuda.stream(out_stream):
+                    out_stream.wait_event(done)
+                    for k in host_out:
+                        m = N_MELS if k == "log_mel" else 1
+                        host_out[k][m * f_lo:m * f_hi].copy_(out[k], non_blocking=True)
+                pending.append((out, d))     # keep device buffers alive until the copies are done
+            if world > 1:
+                dist.all_reduce(st[:, :3], op=dist.ReduceOp.SUM)
+            host_stats.copy_(st, non_blocking=True)
+            out_stream.synchronize()
+            main.synchronize()
+            del pending
+
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        wall = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        e2e_s = float(wall.item())
+        e2e = {"value": world * audio_s * args.steps / e2e_s, "unit": "audio-s/s",
+               "h2d_bytes_per_step": total_samples * 4,
+               "d2h_bytes_per_step": frames_all * 4 * (N_MELS + 4) + 40,
+               "ms_per_step": 1e3 * e2e_s / args.steps,
+               "pitch_mean": finalize_pitch_stats(host_stats)["pitch_mean"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    hbm_peak, peak_src = measured_peaks()
+    per = {k: (kms[i] / max(1, args.steps)) for i, k in enumerate(KERNEL_NAMES)}       # ms per step
+    frames = int((1 + lens_h // HOP).sum())
+    samples = int(lens_h.sum())
+    prior_elems = int(((1 + lens_h // HOP) * text_lens.astype(np.int64)).sum())
+    # algorithmic HBM bytes per step of each kernel (inputs it must read + final outputs it must write;
+    # scratch excluded) -- DESIGN.md section 4
+    alg = {
+        "stft_mel": 4 * samples + 4 * (N_MELS + 1) * frames,
+        "pyin_cmnd": 4 * samples,
+        "pyin_probs": 4 * frames,
+        "viterbi": 0,
+        "backtrack": 8 * frames,
+        "prior": 4 * prior_elems,
+        "stats": 4 * frames,
+    }
+    dom = max(("stft_mel", "pyin_cmnd", "pyin_probs", "viterbi", "backtrack", "prior"), key=lambda k: per[k])
+    # the pYIN chain is one logical kernel split at two scratch hand-offs: its algorithmic traffic is
+    # the audio in (4*hop B/frame) and f0 / flag / prob out (12 B/frame)
+    pyin_alg = 4 * samples + 12 * frames
+    if dom in ("pyin_cmnd", "pyin_probs", "viterbi", "backtrack"):
+        dom_alg, dom_ms = pyin_alg, per["pyin_cmnd"] + per["pyin_probs"] + per["viterbi"] + per["backtrack"]
+        dom_name = "pyin chain (pyin_cmnd + pyin_probs + viterbi + backtrack); slowest member: " + dom
+    else:
+        dom_alg, dom_ms, dom_name = alg[dom], per[dom], dom
+    n_launch = max(1, len(bounds))
+    achieved = dom_alg / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_alg // n_launch, "ms_per_launch": dom_ms / n_launch,
+                "note": "FP64-pipe / latency bound, not HBM bound (DESIGN.md section 4); "
+                        "frac is the honest HBM fraction of its algorithmic bytes"}
+    path_bytes = 4 * samples + 4 * (N_MELS + 4) * frames + 4 * prior_elems
+    step_ms = total_ms / args.steps
+    value = world * audio_s * args.steps / (total_ms * 1e-3)
+    line = {
+        "metric": "audio-seconds processed/sec (sup-data extraction)", "value": value, "unit": "audio-s/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "utterances_per_gpu": n_utts, "audio_hours_per_gpu": audio_s / 3600,
+                   "sup_data_types": ["log_mel", "align_prior_matrix", "pitch", "voiced_mask", "p_voiced", "energy"],
+                   "l2": "inputs larger than L2 (%.1f GB audio per pass)" % (samples * 4 / 1e9),
+                   "parallelism": f"utterance shards x{world}, one all-reduce of pitch partials"},
+        "x_realtime_per_gpu": value / world,
+        "gpu_launches": launches, "clocks": clocks,
+        "kernels_ms_per_step": {k: round(v, 4) for k, v in per.items() if v > 0},
+        "roofline": roofline,
+        "roofline_path": {"bound": "hbm", "achieved": path_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                          "unit": "GB/s", "frac": path_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
+                          "algorithmic_bytes_per_step": path_bytes},
+        "pitch_stats": pstats,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

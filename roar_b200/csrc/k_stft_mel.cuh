@@ -39,7 +39,7 @@ struct StftParams {
   int32_t P, G;               // threads per frame, frames in flight
   // options
   float floor_, mag_power, log_guard, preemph;
-  int32_t log_mode, has_preemph, use_tma;
+  int32_t log_mode, has_preemph, use_tma, preemph_after_pad;
   // tables (device memory)
   const float* window;        // [n_fft]
   const cf32* tw;             // [M]    W_M^k
@@ -114,15 +114,30 @@ HD bool stft_locate(const StftParams& p, int tile, StftTile* t) {
   return true;
 }
 
-HD float stft_sample(const StftParams& p, const StftTile& t, int64_t pos) {
-  // reflect (no edge repeat) into [0, L)
-  int64_t q = pos;
-  const int64_t L = t.L;
+HD int64_t stft_reflect(int64_t q, int64_t L) {
+  // reflect (no edge repeat) into [0, L); -1 when out of reach (L <= pad, rejected by the host)
   if (q < 0) q = -q;
   if (q >= L) q = 2 * (L - 1) - q;
-  if (q < 0 || q >= L) return 0.f;  // only reachable when L <= pad (rejected by the host)
+  return (q < 0 || q >= L) ? -1 : q;
+}
+
+HD float stft_sample(const StftParams& p, const StftTile& t, int64_t pos) {
+  const int64_t q = stft_reflect(pos, t.L);
+  if (q < 0) return 0.f;
   float v = p.audio[t.off + q];
-  if (p.has_preemph && q >= 1) v = v - p.preemph * p.audio[t.off + q - 1];
+  if (p.has_preemph) {
+    if (p.preemph_after_pad) {
+      // FilterbankFeatures with exact_pad pads first and pre-emphasises the PADDED signal
+      // (features.py:387-400): the previous sample is the previous padded sample
+      if (pos > -(int64_t)p.pad_left) {
+        const int64_t q1 = stft_reflect(pos - 1, t.L);
+        if (q1 >= 0) v = v - p.preemph * p.audio[t.off + q1];
+      }
+    } else if (q >= 1) {
+      // center=True: pre-emphasis on the raw signal, torch.stft reflects the result
+      v = v - p.preemph * p.audio[t.off + q - 1];
+    }
+  }
   return v;
 }
 

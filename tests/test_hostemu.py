@@ -55,6 +55,22 @@ def test_emu_fbank_front_matches_oracle_pre_normalisation():
     assert (np.abs(lm - ref[0]) / np.maximum(1, np.abs(ref[0]))).max() <= 1e-4
 
 
+def test_emu_fbank_exact_pad_preemph_order():
+    """exact_pad pads first and pre-emphasises the padded signal (features.py:387-400)."""
+    from roar_b200.config import FLOAT32_TINY
+    y = _wav(1, 12000, sr=16000, seed=5)
+    cfg = SupConfig(sample_rate=16000, n_fft=512, win_length=400, hop_length=160, n_mels=64, highfreq=None,
+                    mel_norm=None, spec_floor=0.0, mag_power=2.0, log_mode="clamp", log_guard=FLOAT32_TINY,
+                    exact_pad=True, preemph=0.97, pyin_frame_length=512)
+    lm, _ = hostemu.logmel_energy(cfg, y)
+    ref, rl = ofbank.FilterbankFeaturesOracle(sample_rate=16000, n_window_size=400, n_window_stride=160, nfilt=64,
+                                              n_fft=512, exact_pad=True, normalize=None,
+                                              log_zero_guard_type="clamp", log_zero_guard_value="tiny", pad_to=0,
+                                              mel_norm=None).forward(y[None, :], [len(y)])
+    assert lm.shape == ref[0].shape == (64, 12000 // 160)
+    assert (np.abs(lm - ref[0]) / np.maximum(1, np.abs(ref[0]))).max() <= 1e-4
+
+
 @pytest.mark.parametrize("i,n", [(0, 44100), (1, 30000), (2, 9000)])
 def test_emu_pyin_equals_oracle(i, n):
     cfg = SupConfig(highfreq=8000.0)
