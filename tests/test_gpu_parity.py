@@ -320,3 +320,56 @@ def test_fbank_vs_reference_golden(golden_dir):
         # gate the bulk at 1e-4 and the tail at 1e-3
         assert np.quantile(err, 0.999) <= 1e-4, (name, float(np.quantile(err, 0.999)))
         assert err.max() <= 2e-3, (name, float(err.max()))
+
+
+def test_cli_cache_layout_and_stats(tmp_path, capsys):
+    """extract_sup_data drop-in: .pt layout / naming / dtypes, idempotent re-run, PITCH_* lines."""
+    import json
+    from scipy.io import wavfile
+    from oracle import extract as oextract, stats as ostats
+    from roar_b200 import extract_sup_data as X, synth
+    man = synth.corpus_manifest("C1", 5)
+    wav_dir = tmp_path / "wavs"
+    paths = []
+    for i, u in enumerate(man):
+        y = synth.synth_utterance(1234, u.utt_id, min(u.n_samples, 22050 * 2), 22050, u.speaker)
+        p = wav_dir / f"spk{u.speaker}" / f"utt{i}.wav"
+        p.parent.mkdir(parents=True, exist_ok=True)
+        wavfile.write(p, 22050, y)
+        paths.append((p, y, u))
+    mf = tmp_path / "train.json"
+    with open(mf, "w") as f:
+        for p, y, u in paths:
+            f.write(json.dumps({"audio_filepath": str(p), "duration": len(y) / 22050, "text": "x" * (u.text_len - 2),
+                                "speaker": u.speaker}) + "\n")
+    sup = tmp_path / "sup"
+    argv = [f"manifest_filepath={mf}", f"sup_data_path={sup}",
+            "sup_data_types=[align_prior_matrix,pitch,voiced_mask,p_voiced,energy,log_mel]"]
+    res = X.main(argv)
+    out = capsys.readouterr().out
+    assert "PITCH_MEAN=" in out and "PITCH_STD=" in out and "PITCH_MIN=" in out and "PITCH_MAX=" in out
+    base = X.get_base_dir([str(p) for p, _, _ in paths])
+    pitches = []
+    for p, y, u in paths:
+        uid = X.rel_audio_id(str(p), base)
+        assert uid == f"spk{u.speaker}_{p.stem}"
+        ref = oextract.extract_utterance(y, u.text_len, dense_viterbi=False)
+        lm = torch.load(sup / "log_mel" / f"{uid}.pt")
+        assert lm.dtype == torch.float32 and tuple(lm.shape) == (1, 80, 1 + len(y) // 256) and not lm.is_cuda
+        assert (np.abs(lm.numpy() - ref["log_mel"]) / np.maximum(1, np.abs(ref["log_mel"]))).max() <= 1e-4
+        for t in ("pitch", "voiced_mask", "p_voiced", "energy"):
+            v = torch.load(sup / t / f"{uid}.pt")
+            assert v.dtype == torch.float32 and v.ndim == 1 and v.numel() == 1 + len(y) // 256
+        assert np.array_equal(torch.load(sup / "pitch" / f"{uid}.pt").numpy(), ref["pitch"])
+        assert np.array_equal(torch.load(sup / "voiced_mask" / f"{uid}.pt").numpy(), ref["voiced_mask"])
+        np.testing.assert_allclose(torch.load(sup / "energy" / f"{uid}.pt").numpy(), ref["energy"], rtol=1e-4)
+        pitches.append(ref["pitch"])
+    ref_stats = ostats.pitch_stats_f64(pitches)
+    assert abs(res["pitch_mean"] / ref_stats["mean"] - 1) < 1e-5 and abs(res["pitch_std"] / ref_stats["std"] - 1) < 1e-5
+    table = json.load(open(sup / "pitch_stats.json"))
+    assert "default" in table and abs(table["default"]["pitch_mean"] / ref_stats["mean"] - 1) < 1e-5
+    # idempotent: a second run recomputes nothing (files untouched) and reports the same statistics
+    mt = {p: os.path.getmtime(p) for p in (sup / "pitch").iterdir()}
+    res2 = X.main(argv)
+    assert all(os.path.getmtime(p) == t for p, t in mt.items())
+    assert abs(res2["pitch_mean"] - res["pitch_mean"]) < 1e-9 and abs(res2["pitch_std"] - res["pitch_std"]) < 1e-9

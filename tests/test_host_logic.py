@@ -1,0 +1,152 @@
+"""CPU tests of the host-side logic of the extraction driver (no GPU): config overrides, manifest
+handling, cache naming, sharding, statistics and the world_size-2 exchange step on gloo."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from roar_b200 import extract_sup_data as X
+from roar_b200.config import SupConfig
+from roar_b200.extractor import finalize_pitch_stats, pack_layout
+
+
+def test_overrides_and_interpolation(tmp_path):
+    cfg = X.load_config(["manifest_filepath=a.json", "sup_data_path=out", "sup_data_types=[pitch,energy,log_mel]",
+                         "dataset.sample_rate=44100", "dataset.n_fft=2048", "dataset.hop_length=512",
+                         "dataset.win_length=2048", "dataset.highfreq=null", "dataloader_params.num_workers=4"])
+    assert cfg["sup_data_types"] == ["pitch", "energy", "log_mel"]
+    assert cfg["dataset"]["sample_rate"] == 44100 and cfg["dataset"]["highfreq"] is None
+    s = X.sup_config_from(cfg)
+    assert (s.sample_rate, s.n_fft, s.hop, s.win, s.highfreq) == (44100, 2048, 512, 2048, None)
+    y = tmp_path / "ds.yaml"
+    y.write_text("name: ds_for_fastpitch_align\nmanifest_filepath: m.json\nsup_data_path: sd\n"
+                 "sup_data_types: [align_prior_matrix, pitch]\n"
+                 "dataset:\n  manifest_filepath: ${manifest_filepath}\n  sup_data_path: ${sup_data_path}\n"
+                 "  sample_rate: 22050\n  n_fft: 1024\n  hop_length: 256\n  win_length: 1024\n  n_mels: 80\n"
+                 "  highfreq: 8000\n")
+    cfg = X.load_config([f"--config-path={tmp_path}", "--config-name=ds", "manifest_filepath=zz.json"])
+    assert cfg["dataset"]["manifest_filepath"] == "zz.json" and cfg["dataset"]["sup_data_path"] == "sd"
+
+
+def test_default_config_matches_reference_yaml_values():
+    s = X.sup_config_from(X.load_config([]))
+    assert (s.sample_rate, s.n_fft, s.win, s.hop, s.n_mels, s.lowfreq, s.highfreq) == (22050, 1024, 1024, 256, 80, 0.0, 8000.0)
+    assert s.pitch_fmin == pytest.approx(65.40639132514966) and s.pitch_fmax == pytest.approx(2093.004522404789)
+    assert s.pyin_frame == 1024 and s.pyin_hop == 256   # pyin ignores hop_length: frame_length // 4
+
+
+def test_ids_base_dir_and_manifest(tmp_path):
+    paths = [tmp_path / "spk1" / "a" / "u1.wav", tmp_path / "spk1" / "u2.wav", tmp_path / "spk2" / "u3.wav"]
+    base = X.get_base_dir([str(p) for p in paths])
+    assert base == tmp_path
+    assert X.rel_audio_id(str(paths[0]), base) == "spk1_a_u1"
+    assert X.rel_audio_id(str(paths[2]), base) == "spk2_u3"
+    m = tmp_path / "m.json"
+    with open(m, "w") as f:
+        for p, d in zip(paths, [0.05, 3.0, 30.0]):
+            f.write(json.dumps({"audio_filepath": str(p), "duration": d, "text": "abc"}) + "\n")
+    items = X.read_manifest(str(m), min_duration=0.1, max_duration=20.0)
+    assert [Path_stem(i) for i in items] == ["u2"]
+    assert X.text_length({"text": "hello"}) == 7 and X.text_length({"text_tokens": [1, 2, 3]}) == 3
+
+
+def Path_stem(item):
+    return os.path.splitext(os.path.basename(item["audio_filepath"]))[0]
+
+
+def test_sharding_partitions_and_balances():
+    rng = np.random.default_rng(0)
+    durs = rng.uniform(0.5, 20.0, size=1001)
+    for world in (1, 2, 4, 8):
+        shards = [X.shard_indices(durs, world, r) for r in range(world)]
+        allidx = np.concatenate(shards)
+        assert len(allidx) == len(durs) and len(set(allidx.tolist())) == len(durs)
+        tot = np.array([durs[s].sum() for s in shards])
+        assert tot.max() / tot.min() < 1.02
+    b = X.make_batches(np.array([10, 50, 20, 40, 30]), 60)
+    assert sorted(np.concatenate(b).tolist()) == [0, 1, 2, 3, 4]
+    assert all(sum([10, 50, 20, 40, 30][i] for i in g) <= 60 or len(g) == 1 for g in b)
+
+
+def test_pack_layout_alignment():
+    offs, total = pack_layout(np.array([5, 8, 1, 13]))
+    assert offs.tolist() == [0, 8, 16, 20] and total == 36 and all(o % 4 == 0 for o in offs)
+
+
+def test_partials_and_stats_match_oracle():
+    from oracle import stats as ostats
+    rng = np.random.default_rng(1)
+    ps = [np.where(rng.random(300) < 0.6, rng.uniform(80, 300, 300), 0).astype(np.float32) for _ in range(9)]
+    t = X.empty_partials(1)
+    for p in ps:
+        t[0] = X.merge_partials(t[0], torch.from_numpy(X.partials_from_pitch(p)))
+    got = X.stats_from_partials(t[0])
+    ref = ostats.pitch_stats_f64(ps)
+    assert got["pitch_mean"] == pytest.approx(ref["mean"], rel=1e-12)
+    assert got["pitch_std"] == pytest.approx(ref["std"], rel=1e-10)
+    assert got["pitch_min"] == ref["min"] and got["pitch_max"] == ref["max"]
+    assert finalize_pitch_stats(t)["pitch_std"] == pytest.approx(ref["std"], rel=1e-10)
+    ref32 = ostats.pitch_stats(ps)
+    assert got["pitch_mean"] == pytest.approx(ref32["mean"], rel=1e-5)
+    assert got["pitch_std"] == pytest.approx(ref32["std"], rel=1e-5)
+    assert X.stats_from_partials(X.empty_partials(1)[0]) is None
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    durs = rng.uniform(1, 10, 40)
+    pitches = [np.where(rng.random(200) < 0.7, rng.uniform(80, 300, 200), 0).astype(np.float32) for _ in durs]
+    mine = X.shard_indices(durs, world, rank)
+    t = X.empty_partials(3)
+    for i in mine:
+        part = torch.from_numpy(X.partials_from_pitch(pitches[i]))
+        t[0] = X.merge_partials(t[0], part)
+        t[1 + i % 2] = X.merge_partials(t[1 + i % 2], part)
+    red = X.allreduce_partials(t)
+    q.put((rank, red.numpy().tolist()))
+    dist.destroy_process_group()
+
+
+def test_allreduce_partials_world2_gloo():
+    import torch.multiprocessing as mp
+    from oracle import stats as ostats
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == res[1]          # every rank ends with the global statistics
+    rng = np.random.default_rng(7)
+    durs = rng.uniform(1, 10, 40)
+    pitches = [np.where(rng.random(200) < 0.7, rng.uniform(80, 300, 200), 0).astype(np.float32) for _ in durs]
+    ref = ostats.pitch_stats_f64(pitches)
+    got = X.stats_from_partials(res[0][0])
+    assert got["pitch_mean"] == pytest.approx(ref["mean"], rel=1e-12)
+    assert got["pitch_std"] == pytest.approx(ref["std"], rel=1e-10)
+    assert got["pitch_min"] == ref["min"] and got["pitch_max"] == ref["max"]
+    even = ostats.pitch_stats_f64([p for i, p in enumerate(pitches) if i % 2 == 0])
+    assert X.stats_from_partials(res[0][1])["pitch_mean"] == pytest.approx(even["mean"], rel=1e-12)
+
+
+def test_wav_decode_int16_and_float(tmp_path):
+    from scipy.io import wavfile
+    x = (np.sin(np.arange(2000) / 7.0) * 0.5).astype(np.float32)
+    wavfile.write(tmp_path / "f.wav", 22050, x)
+    wavfile.write(tmp_path / "i.wav", 22050, (x * 32767).astype(np.int16))
+    a = X.load_wav(str(tmp_path / "f.wav"), 22050)
+    b = X.load_wav(str(tmp_path / "i.wav"), 22050)
+    assert a.dtype == np.float32 and np.array_equal(a, x) and np.abs(b - x).max() < 1e-4
+    with pytest.raises(ValueError):
+        X.load_wav(str(tmp_path / "f.wav"), 16000)
