@@ -6,11 +6,30 @@
 //     y    = DFT_R(v)
 //     out[(j-k)*R + k + q*Ns] = y[q]                    q = 0..R-1
 // After passes whose radices multiply to M the output is in natural order.
-// `tw` is the master table W_M^k = exp(-2*pi*i*k/M), k in [0, M) (built on the host in float64).
+//
+// Bank conflicts: the Ns = 1 pass stores with a stride of R elements, which lands every lane of a
+// warp on the same banks.  All buffers are therefore addressed through pidx(m) = m + (m >> 3)
+// (one pad element per 8), which makes every access pattern of every pass conflict-free for 8-byte
+// and 16-byte elements.  Twiddles come from per-pass tables laid out [r-1][k] (k contiguous across
+// lanes), built on the host in float64 and read through L1 (read-only path).
 #pragma once
 #include "common.cuh"
 
 namespace roar {
+
+HD int pidx(int m) { return m + (m >> 3); }
+
+template <class C> HD C ld_ro(const C* p) { return *p; }
+#if defined(__CUDA_ARCH__)
+template <> __device__ __forceinline__ cf32 ld_ro<cf32>(const cf32* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  cf32 r; r.x = v.x; r.y = v.y; return r;
+}
+template <> __device__ __forceinline__ cf64 ld_ro<cf64>(const cf64* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  cf64 r; r.x = v.x; r.y = v.y; return r;
+}
+#endif
 
 template <bool INV, class C> HD void dft2(C* v) {
   C a = v[0];
@@ -56,15 +75,42 @@ template <int R, bool INV, class C> HD void dftR(C* v) {
   else dft8<INV>(v);
 }
 
-// twiddle + butterfly on values already in registers
+// radix plan for a complex FFT of size M = 2^lg: as many radix-8 passes as possible, then 4 or 2;
+// tw_off[p] = offset of pass p's twiddle block ((R-1)*Ns entries, [r-1][k]) in the per-pass table
+struct FftPlan {
+  int n_pass;
+  int radix[6];
+  int ns[6];
+  int tw_off[6];
+  int tw_total;
+};
+HD FftPlan make_plan(int M) {
+  FftPlan p;
+  p.n_pass = 0;
+  int lg = 0;
+  while ((1 << lg) < M) ++lg;
+  while (lg >= 3) { p.radix[p.n_pass++] = 8; lg -= 3; }
+  if (lg == 2) p.radix[p.n_pass++] = 4;
+  if (lg == 1) p.radix[p.n_pass++] = 2;
+  int ns = 1, off = 0;
+  for (int i = 0; i < p.n_pass; ++i) {
+    p.ns[i] = ns;
+    p.tw_off[i] = off;
+    if (i > 0) off += (p.radix[i] - 1) * ns;
+    ns *= p.radix[i];
+  }
+  p.tw_total = off;
+  return p;
+}
+
+// twiddle (from the pass table `twp`, forward sign; conjugated for the inverse) + butterfly
 template <int R, bool INV, class C>
-HD void stockham_twiddle_dft(C* v, int M, int Ns, int j, const C* tw) {
+HD void stockham_twiddle_dft(C* v, int Ns, int j, const C* twp) {
   if (Ns > 1) {
     const int k = j & (Ns - 1);
-    const int tstep = M / (Ns * R);
 #pragma unroll
     for (int r = 1; r < R; ++r) {
-      C w = tw[r * k * tstep];
+      C w = ld_ro(twp + (r - 1) * Ns + k);
       if (INV) w.y = -w.y;
       v[r] = cmul(v[r], w);
     }
@@ -75,30 +121,14 @@ HD void stockham_twiddle_dft(C* v, int M, int Ns, int j, const C* tw) {
 template <int R, class C> HD void stockham_load(C* v, const C* in, int M, int j) {
   const int stride = M / R;
 #pragma unroll
-  for (int r = 0; r < R; ++r) v[r] = in[j + r * stride];
+  for (int r = 0; r < R; ++r) v[r] = in[pidx(j + r * stride)];
 }
 
 template <int R, class C> HD void stockham_store(const C* v, C* out, int Ns, int j) {
   const int k = j & (Ns - 1);
   const int j0 = (j - k) * R + k;
 #pragma unroll
-  for (int q = 0; q < R; ++q) out[j0 + q * Ns] = v[q];
-}
-
-// radix plan for a complex FFT of size M = 2^lg: as many radix-8 passes as possible, then 4 or 2
-struct FftPlan {
-  int n_pass;
-  int radix[6];
-};
-HD FftPlan make_plan(int M) {
-  FftPlan p;
-  p.n_pass = 0;
-  int lg = 0;
-  while ((1 << lg) < M) ++lg;
-  while (lg >= 3) { p.radix[p.n_pass++] = 8; lg -= 3; }
-  if (lg == 2) p.radix[p.n_pass++] = 4;
-  if (lg == 1) p.radix[p.n_pass++] = 2;
-  return p;
+  for (int q = 0; q < R; ++q) out[pidx(j0 + q * Ns)] = v[q];
 }
 
 }  // namespace roar

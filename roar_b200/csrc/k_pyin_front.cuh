@@ -30,7 +30,9 @@ struct PyinParams {
   int32_t npb, nbps, kmax, n_thr;
   double sr, fmin, no_trough_prob;
   // tables
-  const cf64* tw;             // [F] W_F^k (float64)
+  const cf64* tw;             // [F] W_F^k (float64), read through L1 (inverse packing)
+  const cf64* tw_f;           // per-pass Stockham twiddles, size F (fft.cuh layout)
+  const cf64* tw_h;           // per-pass Stockham twiddles, size F/2
   const double* thresholds;   // [n_thr+1]
   const double* beta_probs;   // [n_thr]
   const double* beta_cum;     // [n_thr+1]
@@ -48,8 +50,7 @@ struct PyinParams {
 
 struct CmndSmem {
   float* audio;    // [span]
-  cf64* tw;        // [F]
-  cf64* buf;       // [G][F]
+  cf64* buf;       // [G][pidx(F)]
   float* E;        // [FT][max_period+1]
   double* d;       // [G][max_period+1]   difference function, then chunk-local prefix sums
   double* dsum;    // [G][max_period+1]
@@ -61,8 +62,7 @@ HD size_t cmnd_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 HD size_t cmnd_smem_carve(const PyinParams& p, unsigned char* base, CmndSmem* s) {
   size_t o = 0;
 #define CARVE(field, type, count) { if (s) s->field = (type*)(base + o); o = cmnd_align16(o + sizeof(type) * (size_t)(count)); }
-  CARVE(tw, cf64, p.F)
-  CARVE(buf, cf64, (size_t)p.G * p.F)
+  CARVE(buf, cf64, (size_t)p.G * pidx(p.F) + 8)
   CARVE(d, double, (size_t)p.G * (p.max_period + 1))
   CARVE(dsum, double, (size_t)p.G * (p.max_period + 1))
   CARVE(chunk, double, (size_t)p.G * 64)
@@ -96,7 +96,6 @@ HD bool pyin_locate(const PyinParams& p, int tile, PyinTile* t) {
 }
 
 HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int tid, int nthr) {
-  for (int i = tid; i < p.F; i += nthr) s.tw[i] = p.tw[i];
   const int n = (t.nf - 1) * p.hop + p.F;
   for (int i = tid; i < n; i += nthr) {
     const int64_t q = t.p0 + i;
@@ -108,6 +107,15 @@ HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
 // per frame; keeps only what the difference function needs: E[tau] = cs[W+tau] - cs[tau].
 // The frames of a tile are spread over warps (lane 0/1 of each) so the strided reads do not pile
 // onto one bank.
+HD float f32_sq_add(float cs, float y) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(cs, __fmul_rn(y, y));
+#else
+  volatile float sq = y * y;
+  volatile float r = cs + sq;
+  return r;
+#endif
+}
 HD void cmnd_phase_energy(const PyinParams& p, const PyinTile& t, CmndSmem& s, int tid, int nthr) {
   const int nwarp = nthr / 32 > 0 ? nthr / 32 : 1;
   const int warp = tid / 32, lane = tid % 32;
@@ -115,25 +123,31 @@ HD void cmnd_phase_energy(const PyinParams& p, const PyinTile& t, CmndSmem& s, i
   if (lane >= (p.FT + nwarp - 1) / nwarp || f >= t.nf) return;
   const float* y = s.audio + f * p.hop;
   float* E = s.E + (size_t)f * (p.max_period + 1);
-  // pass 1: cs[tau] for tau <= max_period kept in E (temporarily)
+  // three straight loops (no load/store aliasing inside a loop, so the loads pipeline):
+  //   A: cs[n] for n <= max_period, kept in E;  B: keep accumulating up to W-1;
+  //   C: n = W + tau: E[tau] = cs[W+tau] - cs[tau]
   float cs = 0.f;
-  const int last = p.W + p.max_period;
-  for (int n = 0; n <= last; ++n) {
-#if defined(__CUDA_ARCH__)
-    cs = __fadd_rn(cs, __fmul_rn(y[n], y[n]));
-#else
-    { volatile float sq = y[n] * y[n]; cs = cs + sq; }
-#endif
-    if (n <= p.max_period) E[n] = cs;
-    if (n >= p.W) {
-#if defined(__CUDA_ARCH__)
-      float e = __fsub_rn(cs, E[n - p.W]);
-#else
-      float e = cs - E[n - p.W];
-#endif
-      if (fabsf(e) < 1e-6f) e = 0.f;
-      E[n - p.W] = e;   // cs[n-W] is not needed again (n-W < W always since max_period < W)
+  int n = 0;
+  for (; n <= p.max_period && n < p.W; ++n) { cs = f32_sq_add(cs, y[n]); E[n] = cs; }
+  for (; n < p.W; ++n) cs = f32_sq_add(cs, y[n]);
+  for (int tau = 0; tau <= p.max_period; ++tau) {
+    cs = f32_sq_add(cs, y[p.W + tau]);
+    if (p.W + tau <= p.max_period) {   // only when max_period >= W (non-default win_length)
+      const float keep = cs;
+      const float lo0 = E[tau];
+      E[p.W + tau] = keep;
+      float e0 = cs - lo0;
+      if (fabsf(e0) < 1e-6f) e0 = 0.f;
+      E[tau] = e0;
+      continue;
     }
+#if defined(__CUDA_ARCH__)
+    float e = __fsub_rn(cs, E[tau]);
+#else
+    float e = cs - E[tau];
+#endif
+    if (fabsf(e) < 1e-6f) e = 0.f;
+    E[tau] = e;
   }
 }
 
@@ -143,7 +157,7 @@ HD void cmnd_first_pass(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
   const int f = g * p.G + slot;
   if (f >= t.nf) return;
   const float* y = s.audio + f * p.hop;
-  cf64* out = s.buf + (size_t)slot * p.F;
+  cf64* out = s.buf + (size_t)slot * pidx(p.F);
   const int nb = p.F / 8;
   for (int j = u; j < nb; j += p.P) {
     cf64 v[8];
@@ -162,7 +176,7 @@ HD void cmnd_first_pass(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
 // Each thread owns at most 8/R butterflies (M/P <= 8), fully unrolled so `regs` stays in registers.
 template <int R, bool INV>
 HD void cmnd_pass_compute(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid, int M,
-                          int Ns, int tw_stride, const cf64* in_base, size_t slot_stride, cf64* regs) {
+                          int Ns, const cf64* twp, const cf64* in_base, size_t slot_stride, cf64* regs) {
   const int slot = tid / p.P, u = tid - slot * p.P;
   const int f = g * p.G + slot;
   if (f >= t.nf) return;
@@ -174,17 +188,7 @@ HD void cmnd_pass_compute(const PyinParams& p, const PyinTile& t, CmndSmem& s, i
     if (j < nb) {
       cf64* v = regs + q * R;
       stockham_load<R>(v, in, M, j);
-      if (Ns > 1) {
-        const int k = j & (Ns - 1);
-        const int tstep = (M / (Ns * R)) * tw_stride;
-#pragma unroll
-        for (int r = 1; r < R; ++r) {
-          cf64 w = s.tw[r * k * tstep];
-          if (INV) w.y = -w.y;
-          v[r] = cmul(v[r], w);
-        }
-      }
-      dftR<R, INV>(v);
+      stockham_twiddle_dft<R, INV>(v, Ns, j, twp);
     }
   }
 }
@@ -209,38 +213,38 @@ HD void cmnd_phase_product(const PyinParams& p, const PyinTile& t, CmndSmem& s, 
   const int slot = tid / p.P, u = tid - slot * p.P;
   const int f = g * p.G + slot;
   if (f >= t.nf) return;
-  cf64* Z = s.buf + (size_t)slot * p.F;
+  cf64* Z = s.buf + (size_t)slot * pidx(p.F);
   for (int k = u; k <= p.H; k += p.P) {
-    const cf64 zk = Z[k];
-    const cf64 zc = cconj(Z[(p.F - k) & (p.F - 1)]);
+    const cf64 zk = Z[pidx(k)];
+    const cf64 zc = cconj(Z[pidx((p.F - k) & (p.F - 1))]);
     cf64 A, B;
     A.x = 0.5 * (zk.x + zc.x); A.y = 0.5 * (zk.y + zc.y);
     B.x = 0.5 * (zk.y - zc.y); B.y = -0.5 * (zk.x - zc.x);   // (zk - zc)/(2i)
-    Z[k] = cmul(A, B);
+    Z[pidx(k)] = cmul(A, B);
   }
 }
 HD void cmnd_phase_pack_inverse(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid) {
   const int slot = tid / p.P, u = tid - slot * p.P;
   const int f = g * p.G + slot;
   if (f >= t.nf) return;
-  cf64* C = s.buf + (size_t)slot * p.F;
+  cf64* C = s.buf + (size_t)slot * pidx(p.F);
   for (int k = u; k <= p.H / 2; k += p.P) {
     const int k2 = p.H - k;
-    const cf64 ck = C[k], c2 = C[k2];
+    const cf64 ck = C[pidx(k)], c2 = C[pidx(k2)];
     // k
     {
       cf64 a = cadd(ck, cconj(c2)), b = csub(ck, cconj(c2));
-      cf64 w = s.tw[k]; w.y = -w.y;                  // e^{+2 pi i k / F}
+      cf64 w = ld_ro(p.tw + k); w.y = -w.y;          // e^{+2 pi i k / F}
       cf64 wb = cmul(w, b);
       cf64 r; r.x = a.x - wb.y; r.y = a.y + wb.x;    // a + i*wb
-      C[k] = r;
+      C[pidx(k)] = r;
     }
     if (k2 != k && k2 < p.H) {
       cf64 a = cadd(c2, cconj(ck)), b = csub(c2, cconj(ck));
-      cf64 w = s.tw[k2]; w.y = -w.y;
+      cf64 w = ld_ro(p.tw + k2); w.y = -w.y;
       cf64 wb = cmul(w, b);
       cf64 r; r.x = a.x - wb.y; r.y = a.y + wb.x;
-      C[k2] = r;
+      C[pidx(k2)] = r;
     }
   }
 }
@@ -251,12 +255,14 @@ HD void cmnd_phase_diff(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
   const int slot = tid / p.P, u = tid - slot * p.P;
   const int f = g * p.G + slot;
   if (f >= t.nf) return;
-  const double* r = (const double*)(z2_base + (size_t)slot * p.F);
+  const cf64* z2 = z2_base + (size_t)slot * pidx(p.F);
   const float* E = s.E + (size_t)f * (p.max_period + 1);
   double* d = s.d + (size_t)slot * (p.max_period + 1);
   const double scale = 1.0 / p.F;
   for (int tau = u; tau <= p.max_period; tau += p.P) {
-    double acf = r[p.W + tau] * scale;
+    const int m = p.W + tau;
+    const cf64 zz = z2[pidx(m >> 1)];
+    double acf = ((m & 1) ? zz.y : zz.x) * scale;
     if (fabs(acf) < 1e-6) acf = 0.0;
 #if defined(__CUDA_ARCH__)
     const float e2 = __fadd_rn(E[0], E[tau]);
@@ -319,8 +325,10 @@ struct ProbSmem {
   uint16_t* sorted;   // [kmax] trough ranks ordered by (c_r, r)
   int16_t* bin;       // [kmax]
   uint8_t* cr;        // [kmax] first threshold index the trough is below (n_thr = never)
-  int32_t* cnt;       // [34]
+  int32_t* cnt;       // [36]
   double* red;        // [32]
+  int32_t* carry;     // [n_thr] troughs of earlier chunks per first-threshold index
+  uint8_t* live;      // [kmax]
 };
 HD size_t prob_smem_carve(const PyinParams& p, unsigned char* base, ProbSmem* s) {
   size_t o = 0;
@@ -329,7 +337,9 @@ HD size_t prob_smem_carve(const PyinParams& p, unsigned char* base, ProbSmem* s)
   CARVE(prob, double, p.kmax)
   CARVE(red, double, 32)
   CARVE(tr, uint16_t, p.kmax)
-  CARVE(sorted, uint16_t, p.kmax)
+  CARVE(sorted, uint16_t, (p.kmax > 2 * p.n_thr ? p.kmax : 2 * p.n_thr) + 2)   // also n_all[n_thr] ints
+  CARVE(carry, int32_t, p.n_thr)
+  CARVE(live, uint8_t, p.kmax)
   CARVE(bin, int16_t, p.kmax)
   CARVE(cr, uint8_t, p.kmax)
   CARVE(cnt, int32_t, 36)
@@ -379,77 +389,113 @@ HD void prob_phase3(const PyinParams& p, ProbSmem& s, int lane, const double* th
   s.red[lane] = best;
   s.cnt[lane] = bi;   // cnt[0..31] reused: per-lane argmin
 }
+// global minimum trough (first index of the minimum height) from the per-lane partials
 HD void prob_phase4(const PyinParams& p, ProbSmem& s, int lane) {
-  const int R = s.cnt[32];
-  // rank of trough r in the order (c_r, r)
-  for (int r = lane; r < R; r += 32) {
-    const int c = s.cr[r];
-    int rank = 0;
-    for (int q = 0; q < R; ++q) {
-      const int cq = s.cr[q];
-      rank += (cq < c || (cq == c && q < r)) ? 1 : 0;
-    }
-    s.sorted[rank] = (uint16_t)r;
+  if (lane != 0) return;
+  double best = 1e300; int bi = 0x7fffffff;
+  for (int v = 0; v < 32; ++v) {
+    const double h = s.red[v]; const int i = s.cnt[v];
+    if (i != 0x7fffffff && (h < best || (h == best && i < bi))) { best = h; bi = i; }
   }
-  if (lane == 0) {   // global minimum trough: first index of the minimum height
-    double best = 1e300; int bi = 0x7fffffff;
-    for (int v = 0; v < 32; ++v) {
-      const double h = s.red[v]; const int i = s.cnt[v];
-      if (i != 0x7fffffff && (h < best || (h == best && i < bi))) { best = h; bi = i; }
+  s.cnt[33] = bi;
+}
+
+// Threshold-beta / Boltzmann probabilities.  Lanes own troughs (chunks of 32 in lag order); the loop
+// over the thresholds c is warp-uniform.  n_c = #{r : c_r <= c} is uniform; pos(r, c) =
+// #{r' < r : c_r' <= c} advances by the number of earlier troughs whose first threshold is c, which
+// is a ballot + popcount inside the chunk plus a per-threshold carry from the previous chunks.
+//   probs_r = sum_{c >= c_r} (fact[n_c] * exp(-lambda * pos)) * beta[c]   (+ no-trough bonus on the global min)
+// `hist` [n_thr] (ints) aliases s.sorted (unused otherwise).
+HD void prob_trough_finish(const PyinParams& p, ProbSmem& s, int r, double acc) {
+  const int cr = s.cr[r];
+  if (r == s.cnt[33]) acc += p.no_trough_prob * p.beta_cum[cr];
+  s.prob[r] = acc;
+  int bin = -1;
+  if (acc != 0.0) {
+    const int i = s.tr[r];
+    double shift = 0.0;
+    if (i > 0 && i < p.n_lags - 1) {
+      const double a = s.x[i + 1] + s.x[i - 1] - 2.0 * s.x[i];
+      const double b = (s.x[i + 1] - s.x[i - 1]) / 2.0;
+      if (!(fabs(b) >= fabs(a))) shift = -b / a;
     }
-    s.cnt[33] = bi;
+    const double period = (double)(p.min_period + i) + shift;
+    const double f0 = p.sr / period;
+    const double bf = (double)(12 * p.nbps) * log2(f0 / p.fmin);
+    double rb = rint(bf);
+    if (rb < 0.0) rb = 0.0;
+    if (rb > (double)p.npb) rb = (double)p.npb;
+    bin = (int)rb;
+  }
+  s.bin[r] = (int16_t)bin;
+}
+
+// n_all[c] = #{r : c_r <= c} over ALL troughs (kept in smem, [n_thr] ints, aliases s.sorted)
+HD void prob_phase5a(const PyinParams& p, ProbSmem& s, int lane) {
+  const int R = s.cnt[32];
+  int* n_all = reinterpret_cast<int*>(s.sorted);
+  for (int c = lane; c < p.n_thr; c += 32) {
+    int n = 0;
+    for (int r = 0; r < R; ++r) n += ((int)s.cr[r] <= c) ? 1 : 0;
+    n_all[c] = n;
   }
 }
-HD void prob_phase5(const PyinParams& p, ProbSmem& s, int lane) {
+// one chunk of 32 troughs; `carry[c]` (ints, [n_thr], aliases s.bin's tail? no: own array s.carry)
+HD void prob_phase5b_lane(const PyinParams& p, ProbSmem& s, int base, int lane, const int* chunk_cr /*[32]*/) {
+  // reference formulation used by the host harness: identical arithmetic, ballot replaced by a scan
   const int R = s.cnt[32];
-  const int gmin = s.cnt[33];
+  const int r = base + lane;
+  if (r >= R) return;
+  const int* n_all = reinterpret_cast<const int*>(s.sorted);
+  const int cr = s.cr[r];
+  double acc = 0.0;
+  int pos = 0;
+  // earlier chunks: every trough r' < base counts when c_r' <= c
+  for (int c = 0; c < p.n_thr; ++c) {
+    int inc = s.carry[c];
+    for (int l = 0; l < lane; ++l) inc += (chunk_cr[l] == c) ? 1 : 0;
+    pos += inc;
+    if (c >= cr) acc += (p.boltz_fact[n_all[c]] * p.boltz_exp[pos]) * p.beta_probs[c];
+  }
+  prob_trough_finish(p, s, r, acc);
+}
+
+// live = survives NumPy's last-write-wins scatter: no later trough with a non-zero probability
+// lands on the same pitch bin (bins are non-increasing in lag order, so only the run of following
+// zero-probability troughs has to be skipped)
+HD void prob_phase6a(const PyinParams& p, ProbSmem& s, int lane) {
+  const int R = s.cnt[32];
   for (int r = lane; r < R; r += 32) {
-    const int cr = s.cr[r];
-    double acc = 0.0;
-    int ptr = 0, n = 0, pos = 0;
-    for (int c = 0; c < p.n_thr; ++c) {
-      while (ptr < R && s.cr[s.sorted[ptr]] == c) { n++; pos += (s.sorted[ptr] < r) ? 1 : 0; ptr++; }
-      if (c >= cr) acc += (p.boltz_fact[n] * p.boltz_exp[pos]) * p.beta_probs[c];
-    }
-    if (r == gmin) acc += p.no_trough_prob * p.beta_cum[cr];
-    s.prob[r] = acc;
-    int bin = -1;
-    if (acc != 0.0) {
-      const int i = s.tr[r];
-      double shift = 0.0;
-      if (i > 0 && i < p.n_lags - 1) {
-        const double a = s.x[i + 1] + s.x[i - 1] - 2.0 * s.x[i];
-        const double b = (s.x[i + 1] - s.x[i - 1]) / 2.0;
-        if (!(fabs(b) >= fabs(a))) shift = -b / a;
+    const int b = s.bin[r];
+    bool live = b >= 0 && b < p.npb;
+    if (live) {
+      for (int q = r + 1; q < R; ++q) {
+        const int bq = s.bin[q];
+        if (bq < 0) continue;
+        live = bq != b;
+        if (live) {
+          // bins are monotone, but stay exact even if they were not: finish the scan
+          for (int q2 = q + 1; q2 < R; ++q2) if (s.bin[q2] == b) { live = false; break; }
+        }
+        break;
       }
-      const double period = (double)(p.min_period + i) + shift;
-      const double f0 = p.sr / period;
-      const double bf = (double)(12 * p.nbps) * log2(f0 / p.fmin);
-      double rb = rint(bf);
-      if (rb < 0.0) rb = 0.0;
-      if (rb > (double)p.npb) rb = (double)p.npb;
-      bin = (int)rb;
     }
-    s.bin[r] = (int16_t)bin;
+    s.live[r] = live ? 1 : 0;
   }
 }
-// lane 0: last-write-wins de-duplication, voiced probability, emit the sparse observation list
-HD void prob_phase6(const PyinParams& p, ProbSmem& s, int64_t frame, int lane) {
+// lane 0: voiced probability (ascending pitch bin = descending lag, like np.sum over the bins) and
+// the compact observation list
+HD void prob_phase6b(const PyinParams& p, ProbSmem& s, int64_t frame, int lane) {
   if (lane != 0) return;
   const int R = s.cnt[32];
   uint16_t* ob = p.cand_bin + (size_t)frame * p.kmax;
   double* ol = p.cand_lp + (size_t)frame * p.kmax;
   int n = 0;
   double vp = 0.0;
-  // descending r = ascending pitch bin (np.sum runs over bins in ascending order)
   for (int r = R - 1; r >= 0; --r) {
-    const int b = s.bin[r];
-    if (b < 0 || b >= p.npb) continue;
-    bool live = true;
-    for (int q = r + 1; q < R; ++q) if (s.bin[q] == b) { live = false; break; }
-    if (!live) continue;
+    if (!s.live[r]) continue;
     vp += s.prob[r];
-    ob[n] = (uint16_t)b;
+    ob[n] = (uint16_t)s.bin[r];
     ol[n] = log(s.prob[r] + 2.2250738585072014e-308);
     ++n;
   }
@@ -474,6 +520,7 @@ __global__ void __launch_bounds__(256) k_pyin_cmnd(const PyinParams p) {
   __syncthreads();
   const FftPlan planF = make_plan(p.F);
   const FftPlan planH = make_plan(p.H);
+  const size_t FP = (size_t)pidx(p.F);
   cf64 regs[8];
   const int n_groups = (t.nf + p.G - 1) / p.G;
   for (int g = 0; g < n_groups; ++g) {
@@ -482,13 +529,14 @@ __global__ void __launch_bounds__(256) k_pyin_cmnd(const PyinParams p) {
     int Ns = 8;
     for (int ps = 1; ps < planF.n_pass; ++ps) {
       const int R = planF.radix[ps];
-      if (R == 8) cmnd_pass_compute<8, false>(p, t, s, g, tid, p.F, Ns, 1, s.buf, p.F, regs);
-      else if (R == 4) { cmnd_pass_compute<4, false>(p, t, s, g, tid, p.F, Ns, 1, s.buf, p.F, regs); }
-      else { cmnd_pass_compute<2, false>(p, t, s, g, tid, p.F, Ns, 1, s.buf, p.F, regs); }
+      const cf64* twp = p.tw_f + planF.tw_off[ps];
+      if (R == 8) cmnd_pass_compute<8, false>(p, t, s, g, tid, p.F, Ns, twp, s.buf, FP, regs);
+      else if (R == 4) { cmnd_pass_compute<4, false>(p, t, s, g, tid, p.F, Ns, twp, s.buf, FP, regs); }
+      else { cmnd_pass_compute<2, false>(p, t, s, g, tid, p.F, Ns, twp, s.buf, FP, regs); }
       __syncthreads();
-      if (R == 8) cmnd_pass_store<8>(p, t, g, tid, p.F, Ns, s.buf, p.F, regs);
-      else if (R == 4) cmnd_pass_store<4>(p, t, g, tid, p.F, Ns, s.buf, p.F, regs);
-      else cmnd_pass_store<2>(p, t, g, tid, p.F, Ns, s.buf, p.F, regs);
+      if (R == 8) cmnd_pass_store<8>(p, t, g, tid, p.F, Ns, s.buf, FP, regs);
+      else if (R == 4) cmnd_pass_store<4>(p, t, g, tid, p.F, Ns, s.buf, FP, regs);
+      else cmnd_pass_store<2>(p, t, g, tid, p.F, Ns, s.buf, FP, regs);
       __syncthreads();
       Ns *= R;
     }
@@ -500,13 +548,14 @@ __global__ void __launch_bounds__(256) k_pyin_cmnd(const PyinParams p) {
     Ns = 1;
     for (int ps = 0; ps < planH.n_pass; ++ps) {
       const int R = planH.radix[ps];
-      if (R == 8) cmnd_pass_compute<8, true>(p, t, s, g, tid, p.H, Ns, 2, s.buf, p.F, regs);
-      else if (R == 4) cmnd_pass_compute<4, true>(p, t, s, g, tid, p.H, Ns, 2, s.buf, p.F, regs);
-      else cmnd_pass_compute<2, true>(p, t, s, g, tid, p.H, Ns, 2, s.buf, p.F, regs);
+      const cf64* twp = p.tw_h + planH.tw_off[ps];
+      if (R == 8) cmnd_pass_compute<8, true>(p, t, s, g, tid, p.H, Ns, twp, s.buf, FP, regs);
+      else if (R == 4) cmnd_pass_compute<4, true>(p, t, s, g, tid, p.H, Ns, twp, s.buf, FP, regs);
+      else cmnd_pass_compute<2, true>(p, t, s, g, tid, p.H, Ns, twp, s.buf, FP, regs);
       __syncthreads();
-      if (R == 8) cmnd_pass_store<8>(p, t, g, tid, p.H, Ns, s.buf, p.F, regs);
-      else if (R == 4) cmnd_pass_store<4>(p, t, g, tid, p.H, Ns, s.buf, p.F, regs);
-      else cmnd_pass_store<2>(p, t, g, tid, p.H, Ns, s.buf, p.F, regs);
+      if (R == 8) cmnd_pass_store<8>(p, t, g, tid, p.H, Ns, s.buf, FP, regs);
+      else if (R == 4) cmnd_pass_store<4>(p, t, g, tid, p.H, Ns, s.buf, FP, regs);
+      else cmnd_pass_store<2>(p, t, g, tid, p.H, Ns, s.buf, FP, regs);
       __syncthreads();
       Ns *= R;
     }
@@ -539,8 +588,32 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
     prob_phase2(p, s, lane); __syncwarp();
     prob_phase3(p, s, lane, thr); __syncwarp();
     prob_phase4(p, s, lane); __syncwarp();
-    prob_phase5(p, s, lane); __syncwarp();
-    prob_phase6(p, s, frame, lane); __syncwarp();
+    prob_phase5a(p, s, lane);
+    for (int c = lane; c < p.n_thr; c += 32) s.carry[c] = 0;
+    __syncwarp();
+    {
+      const int R = s.cnt[32];
+      const int* n_all = reinterpret_cast<const int*>(s.sorted);
+      const unsigned lt_mask = (1u << lane) - 1u;
+      for (int base = 0; base < R; base += 32) {
+        const int r = base + lane;
+        const int cr = r < R ? (int)s.cr[r] : 0x7fff;
+        double acc = 0.0;
+        int pos = 0;
+        for (int c = 0; c < p.n_thr; ++c) {
+          const unsigned m = __ballot_sync(0xffffffffu, cr == c);
+          const int carry = s.carry[c];
+          pos += carry + __popc(m & lt_mask);
+          if (c >= cr) acc += (p.boltz_fact[n_all[c]] * p.boltz_exp[pos]) * p.beta_probs[c];
+          if (lane == 0 && m) s.carry[c] = carry + __popc(m);
+        }
+        if (r < R) prob_trough_finish(p, s, r, acc);
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    prob_phase6a(p, s, lane); __syncwarp();
+    prob_phase6b(p, s, frame, lane); __syncwarp();
   }
 }
 #endif  // __CUDACC__

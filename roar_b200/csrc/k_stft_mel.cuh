@@ -42,8 +42,8 @@ struct StftParams {
   int32_t log_mode, has_preemph, use_tma, preemph_after_pad;
   // tables (device memory)
   const float* window;        // [n_fft]
-  const cf32* tw;             // [M]    W_M^k
-  const cf32* tw_post;        // [M+1]  W_{n_fft}^k
+  const cf32* tw;             // per-pass Stockham twiddles (fft.cuh layout), read through L1
+  const cf32* tw_post;        // [M+1]  W_{n_fft}^k, read through L1
   const int32_t* mel_start;   // [n_mels]
   const int32_t* mel_count;
   const int32_t* mel_offset;
@@ -55,10 +55,8 @@ struct StftParams {
 struct StftSmem {
   float* audio;     // [span]
   float* window;    // [n_fft]
-  cf32* tw;         // [M]
-  cf32* tw_post;    // [M+1]
-  cf32* bufA;       // [G*M]
-  cf32* bufB;       // [G*M]   (spec[G][n_bins] float aliases the buffer not holding the FFT result)
+  cf32* bufA;       // [G*MP]  MP = pidx(M): padded slot stride
+  cf32* bufB;       // [G*MP]  (spec[G][n_bins] float aliases the buffer not holding the FFT result)
   float* part;      // [blockDim] energy partials
   float* out;       // [n_mels][FT+1] staging
   float* en;        // [FT]
@@ -75,10 +73,8 @@ HD size_t stft_smem_carve(const StftParams& p, int nthreads, unsigned char* base
   CARVE(mbar, unsigned long long, 2)
   CARVE(audio, float, p.span)
   CARVE(window, float, p.n_fft)
-  CARVE(tw, cf32, p.M)
-  CARVE(tw_post, cf32, p.M + 1)
-  CARVE(bufA, cf32, (size_t)p.G * p.M + 8)
-  CARVE(bufB, cf32, (size_t)p.G * p.M + 8)
+  CARVE(bufA, cf32, (size_t)p.G * pidx(p.M) + 8)
+  CARVE(bufB, cf32, (size_t)p.G * pidx(p.M) + 8)
   CARVE(part, float, nthreads)
   CARVE(out, float, (size_t)p.n_mels * (p.FT + 1))
   CARVE(en, float, p.FT)
@@ -144,8 +140,6 @@ HD float stft_sample(const StftParams& p, const StftTile& t, int64_t pos) {
 // ---- phase A: tables + audio tile (generic path; the TMA path replaces the audio part on device)
 HD void stft_phase_tables(const StftParams& p, StftSmem& s, int tid, int nthr) {
   for (int i = tid; i < p.n_fft; i += nthr) s.window[i] = p.window[i];
-  for (int i = tid; i < p.M; i += nthr) s.tw[i] = p.tw[i];
-  for (int i = tid; i <= p.M; i += nthr) s.tw_post[i] = p.tw_post[i];
   for (int i = tid; i < p.n_mels; i += nthr) {
     s.mel_start[i] = p.mel_start[i]; s.mel_count[i] = p.mel_count[i]; s.mel_offset[i] = p.mel_offset[i];
   }
@@ -165,7 +159,7 @@ HD void stft_first_pass(const StftParams& p, const StftTile& t, StftSmem& s, int
   const int f = g * p.G + slot;
   if (f >= t.nf) return;
   const float* a = s.audio + f * p.hop;
-  cf32* out = s.bufA + (size_t)slot * p.M;
+  cf32* out = s.bufA + (size_t)slot * pidx(p.M);
   const int nb = p.M / R;
   for (int j = u; j < nb; j += p.P) {
     cf32 v[R];
@@ -182,17 +176,17 @@ HD void stft_first_pass(const StftParams& p, const StftTile& t, StftSmem& s, int
 
 template <int R>
 HD void stft_pass(const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid, int Ns,
-                  const cf32* in_base, cf32* out_base) {
+                  const cf32* twp, const cf32* in_base, cf32* out_base) {
   const int slot = tid / p.P, u = tid - slot * p.P;
   const int f = g * p.G + slot;
   if (f >= t.nf) return;
-  const cf32* in = in_base + (size_t)slot * p.M;
-  cf32* out = out_base + (size_t)slot * p.M;
+  const cf32* in = in_base + (size_t)slot * pidx(p.M);
+  cf32* out = out_base + (size_t)slot * pidx(p.M);
   const int nb = p.M / R;
   for (int j = u; j < nb; j += p.P) {
     cf32 v[R];
     stockham_load<R>(v, in, p.M, j);
-    stockham_twiddle_dft<R, false>(v, p.M, Ns, j, s.tw);
+    stockham_twiddle_dft<R, false>(v, Ns, j, twp);
     stockham_store<R>(v, out, Ns, j);
   }
 }
@@ -210,15 +204,15 @@ HD void stft_phase_post(const StftParams& p, const StftTile& t, StftSmem& s, int
   const int f = g * p.G + slot;
   float esum = 0.f;
   if (f < t.nf) {
-    const cf32* Z = z_base + (size_t)slot * p.M;
-    float* spec = spec_base + (size_t)slot * (2 * p.M);
+    const cf32* Z = z_base + (size_t)slot * pidx(p.M);
+    float* spec = spec_base + (size_t)slot * (2 * pidx(p.M));
     for (int k = u; k <= p.M; k += p.P) {
-      const cf32 zk = Z[k & (p.M - 1)];
-      const cf32 zc = cconj(Z[(p.M - k) & (p.M - 1)]);
+      const cf32 zk = Z[pidx(k & (p.M - 1))];
+      const cf32 zc = cconj(Z[pidx((p.M - k) & (p.M - 1))]);
       // X[k] = (zk+zc)/2 + W_N^k * (zk-zc)/(2i)
       cf32 e; e.x = 0.5f * (zk.x + zc.x); e.y = 0.5f * (zk.y + zc.y);
       cf32 d; d.x = 0.5f * (zk.y - zc.y); d.y = -0.5f * (zk.x - zc.x);   // (zk-zc)/(2i)
-      const cf32 w = s.tw_post[k];
+      const cf32 w = ld_ro(p.tw_post + k);
       const float re = e.x + (w.x * d.x - w.y * d.y);
       const float im = e.y + (w.x * d.y + w.y * d.x);
       const float mag = sqrtf(re * re + im * im + p.floor_);
@@ -244,7 +238,7 @@ HD void stft_phase_mel(const StftParams& p, const StftTile& t, StftSmem& s, int 
       s.en[f] = sqrtf(e);
       continue;
     }
-    const float* spec = spec_base + (size_t)slot * (2 * p.M) + s.mel_start[m];
+    const float* spec = spec_base + (size_t)slot * (2 * pidx(p.M)) + s.mel_start[m];
     const float* wgt = s.mel_w + s.mel_offset[m];
     const int cnt = s.mel_count[m];
     float acc = 0.f;
@@ -272,10 +266,10 @@ HD void stft_phase_store(const StftParams& p, const StftTile& t, StftSmem& s, in
 
 // One FFT pass of radix R over all frames in flight (dispatch on the runtime radix).
 HD void stft_pass_any(int R, const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid,
-                      int Ns, const cf32* src, cf32* dst) {
-  if (R == 8) stft_pass<8>(p, t, s, g, tid, Ns, src, dst);
-  else if (R == 4) stft_pass<4>(p, t, s, g, tid, Ns, src, dst);
-  else stft_pass<2>(p, t, s, g, tid, Ns, src, dst);
+                      int Ns, const cf32* twp, const cf32* src, cf32* dst) {
+  if (R == 8) stft_pass<8>(p, t, s, g, tid, Ns, twp, src, dst);
+  else if (R == 4) stft_pass<4>(p, t, s, g, tid, Ns, twp, src, dst);
+  else stft_pass<2>(p, t, s, g, tid, Ns, twp, src, dst);
 }
 
 #ifdef __CUDACC__
@@ -345,7 +339,7 @@ __global__ void __launch_bounds__(256) k_stft_mel(const StftParams p) {
     const cf32* src = s.bufA;
     cf32* dst = s.bufB;
     for (int ps = 1; ps < plan.n_pass; ++ps) {
-      stft_pass_any(plan.radix[ps], p, t, s, g, tid, Ns, src, dst);
+      stft_pass_any(plan.radix[ps], p, t, s, g, tid, Ns, p.tw + plan.tw_off[ps], src, dst);
       __syncthreads();
       Ns *= plan.radix[ps];
       const cf32* tmp = src; src = dst; dst = const_cast<cf32*>(tmp);

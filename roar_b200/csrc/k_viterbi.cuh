@@ -46,16 +46,18 @@ HD bool vit_better(double v, int k, const VitBest& b) { return v > b.v || (v == 
 
 // One DP step for pitch bin j.  V: previous values as (voiced, unvoiced) pairs; returns the new pair,
 // writes the two back-pointers.  (kstar, vmax) = first global argmax of the previous values.
-HD void vit_step_bin(const VitParams& p, int j, const cf64* V, const double* lt, const uint16_t* row_id,
+// `row_ofs[i]` = row_id[i] * tw (entry offset of source bin i's row in the banded table).
+HD void vit_step_bin(const VitParams& p, int j, const cf64* V, const double* lt, const int32_t* row_ofs,
                      double lp_v, double lp_u, int kstar, double vmax, cf64* vnew, uint16_t* ptr_row) {
   const int lo = j - p.hw < 0 ? 0 : j - p.hw;
   const int hi = j + p.hw > p.npb - 1 ? p.npb - 1 : j + p.hw;
   double b00 = -1e308, b10 = -1e308, b01 = -1e308, b11 = -1e308;   // src block -> dst block
   int a00 = 0, a10 = 0, a01 = 0, a11 = 0;
+  const cf64* lt2 = reinterpret_cast<const cf64*>(lt) + (j + p.hw);
   for (int i = lo; i <= hi; ++i) {
     const cf64 v = V[i];
-    const double* e = lt + ((size_t)row_id[i] * p.tw + (j - i + p.hw)) * 2;
-    const double ls = e[0], lc = e[1];
+    const cf64 e = lt2[row_ofs[i] - i];
+    const double ls = e.x, lc = e.y;
     const double s00 = v.x + ls, s10 = v.y + lc, s01 = v.x + lc, s11 = v.y + ls;
     if (s00 > b00) { b00 = s00; a00 = i; }
     if (s10 > b10) { b10 = s10; a10 = i; }
@@ -103,16 +105,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
   size_t o = 0;
   cf64* Vb = (cf64*)(smem_raw + o);          o += sizeof(cf64) * 2 * (size_t)p.npb;
   double* lpv = (double*)(smem_raw + o);     o += sizeof(double) * 2 * (size_t)p.npb;
-  double* wv = (double*)(smem_raw + o);      o += sizeof(double) * 32;
-  int* wk = (int*)(smem_raw + o);            o += sizeof(int) * 32;
-  uint16_t* rid = (uint16_t*)(smem_raw + o); o += (sizeof(uint16_t) * (size_t)p.npb + 15) & ~(size_t)15;
+  double* wv = (double*)(smem_raw + o);      o += sizeof(double) * 64;   // [2][32] double-buffered
+  int* wk = (int*)(smem_raw + o);            o += sizeof(int) * 64;
+  int32_t* rid = (int32_t*)(smem_raw + o);   o += (sizeof(int32_t) * (size_t)p.npb + 15) & ~(size_t)15;
   double* lts = (double*)(smem_raw + o);
   if (LT_SMEM) {
     const int n = p.n_rows * p.tw * 2;
     for (int i = tid; i < n; i += nthr) lts[i] = p.lt_rows[i];
   }
   const double* lt = LT_SMEM ? lts : p.lt_rows;
-  for (int i = tid; i < p.npb; i += nthr) { rid[i] = p.row_id[i]; lpv[i] = p.lt0; lpv[p.npb + i] = p.lt0; }
+  for (int i = tid; i < p.npb; i += nthr) { rid[i] = (int32_t)p.row_id[i] * p.tw; lpv[i] = p.lt0; lpv[p.npb + i] = p.lt0; }
   __syncthreads();
   // frame 0 observations
   {
@@ -140,9 +142,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
   __syncthreads();
 
   for (int t = 1; t < T; ++t) {
-    // block-wide first argmax of V[t-1]
-    double vmax = lane < nwarp ? wv[lane] : -1e308;
-    int kstar = lane < nwarp ? wk[lane] : 0x7fffffff;
+    // block-wide first argmax of V[t-1]; per-warp partials are double-buffered on step parity so one
+    // barrier per step suffices
+    const int rb = ((t - 1) & 1) * 32, wb = (t & 1) * 32;
+    double vmax = lane < nwarp ? wv[rb + lane] : -1e308;
+    int kstar = lane < nwarp ? wk[rb + lane] : 0x7fffffff;
     vit_warp_argmax(vmax, kstar);
     const cf64* Vc = Vb + (size_t)((t - 1) & 1) * p.npb;
     cf64* Vn = Vb + (size_t)(t & 1) * p.npb;
@@ -159,7 +163,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
     }
     const double lp_u = p.lp_unvoiced[f0 + t];
     bestv = -1e308; bestk = 0x7fffffff;
-    __syncthreads();   // everyone has read wv/wk before they are overwritten below
     if (j < p.npb) {
       cf64 vn;
       vit_step_bin(p, j, Vc, lt, rid, lpc[j], lp_u, kstar, vmax, &vn, p.ptr + (size_t)(f0 + t) * (2 * p.npb));
@@ -170,12 +173,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
     }
     if (tid < nc_next) lpn[nb_bin] = nb_lp;
     vit_warp_argmax(bestv, bestk);
-    if (lane == 0) { wv[warp] = bestv; wk[warp] = bestk; }
+    if (lane == 0) { wv[wb + warp] = bestv; wk[wb + warp] = bestk; }
     __syncthreads();
   }
   if (warp == 0) {
-    double vmax = lane < nwarp ? wv[lane] : -1e308;
-    int kstar = lane < nwarp ? wk[lane] : 0x7fffffff;
+    const int rb = ((T - 1) & 1) * 32;
+    double vmax = lane < nwarp ? wv[rb + lane] : -1e308;
+    int kstar = lane < nwarp ? wk[rb + lane] : 0x7fffffff;
     vit_warp_argmax(vmax, kstar);
     if (lane == 0) p.last_state[utt] = kstar;
   }

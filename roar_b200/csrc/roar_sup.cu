@@ -42,7 +42,7 @@ struct roar_sup_handle {
   int stft_FT = 16, stft_P = 64, stft_G = 4, stft_span = 0; size_t stft_smem = 0;
   int use_tma = 1;
   // K2
-  cf64* d_tw64 = nullptr;
+  cf64 *d_tw64 = nullptr, *d_tw64_f = nullptr, *d_tw64_h = nullptr;
   double *d_thr = nullptr, *d_beta = nullptr, *d_beta_cum = nullptr, *d_bexp = nullptr, *d_bfact = nullptr;
   int pyin_FT = 16, pyin_P = 128, pyin_G = 2, pyin_span = 0; size_t cmnd_smem = 0, prob_smem = 0;
   // K3
@@ -120,7 +120,7 @@ static PyinParams pyin_params_base(const roar_sup_handle* h) {
   p.FT = h->pyin_FT; p.span = h->pyin_span; p.P = h->pyin_P; p.G = h->pyin_G;
   p.npb = g.npb; p.nbps = g.nbps; p.kmax = g.kmax; p.n_thr = g.n_thr;
   p.sr = h->cfg.sample_rate; p.fmin = h->cfg.pitch_fmin; p.no_trough_prob = h->cfg.no_trough_prob;
-  p.tw = h->d_tw64; p.thresholds = h->d_thr; p.beta_probs = h->d_beta; p.beta_cum = h->d_beta_cum;
+  p.tw = h->d_tw64; p.tw_f = h->d_tw64_f; p.tw_h = h->d_tw64_h; p.thresholds = h->d_thr; p.beta_probs = h->d_beta; p.beta_cum = h->d_beta_cum;
   p.boltz_exp = h->d_bexp; p.boltz_fact = h->d_bfact;
   return p;
 }
@@ -206,7 +206,7 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     std::vector<float> win = make_window(*cfg);
     std::vector<float> fb = make_mel_filterbank(*cfg);
     MelRows mr = make_mel_rows(fb, g.n_mels, g.n_bins);
-    std::vector<cf32> tw = make_twiddles<cf32, float>(g.M, g.M);
+    std::vector<cf32> tw = make_pass_twiddles<cf32, float>(g.M);
     std::vector<cf32> twp = make_twiddles<cf32, float>(g.n_fft, g.M + 1);
     UP(win, d_window) UP(tw, d_tw) UP(twp, d_tw_post)
     UP(mr.start, d_mel_start) UP(mr.count, d_mel_count) UP(mr.offset, d_mel_offset) UP(mr.weights, d_mel_w)
@@ -225,7 +225,8 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
   {
     PyinTables t = make_pyin_tables(*cfg, g);
     std::vector<cf64> tw = make_twiddles<cf64, double>(g.pf, g.pf);
-    UP(tw, d_tw64) UP(t.thresholds, d_thr) UP(t.beta_probs, d_beta) UP(t.beta_cum, d_beta_cum)
+    std::vector<cf64> twf = make_pass_twiddles<cf64, double>(g.pf), twh = make_pass_twiddles<cf64, double>(g.pf / 2);
+    UP(tw, d_tw64) UP(twf, d_tw64_f) UP(twh, d_tw64_h) UP(t.thresholds, d_thr) UP(t.beta_probs, d_beta) UP(t.beta_cum, d_beta_cum)
     UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(t.lt_rows, d_lt_rows) UP(t.row_id, d_row_id)
     UP(t.freqs, d_freqs)
     h->n_rows = t.n_rows; h->lt0 = t.lt0; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
@@ -242,8 +243,8 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     CUDA_TRY(cudaFuncSetAttribute(k_pyin_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->prob_smem));
     h->vit_threads = (g.npb + 31) / 32 * 32;
     if (h->vit_threads < g.kmax) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "kmax exceeds Viterbi block size"); }
-    size_t base = sizeof(cf64) * 2 * g.npb + sizeof(double) * 2 * g.npb + sizeof(double) * 32 + sizeof(int) * 32 +
-                  ((sizeof(uint16_t) * g.npb + 15) & ~(size_t)15) + 128;
+    size_t base = sizeof(cf64) * 2 * g.npb + sizeof(double) * 2 * g.npb + sizeof(double) * 64 + sizeof(int) * 64 +
+                  ((sizeof(int32_t) * g.npb + 15) & ~(size_t)15) + 128;
     size_t ltb = sizeof(double) * 2 * (size_t)t.n_rows * g.tw;
     h->lt_in_smem = base + ltb <= h->max_smem ? 1 : 0;
     h->vit_smem = base + (h->lt_in_smem ? ltb : 0);

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/roar_sup.h"
+#include "fft.cuh"
 
 namespace roar {
 
@@ -172,6 +173,24 @@ inline std::vector<T2> make_twiddles(int n, int count, double sign = -1.0) {
     double a = sign * 2.0 * kPi * k / n;
     t[k].x = (T)std::cos(a);
     t[k].y = (T)std::sin(a);
+  }
+  return t;
+}
+
+// per-pass Stockham twiddles, layout of fft.cuh's FftPlan: pass p >= 1 holds [(r-1)*Ns + k] =
+// exp(-2*pi*i*r*k/(Ns*R)), computed directly in float64
+template <class T2, class T>
+inline std::vector<T2> make_pass_twiddles(int M) {
+  FftPlan plan = make_plan(M);
+  std::vector<T2> t(plan.tw_total > 0 ? plan.tw_total : 1);
+  for (int p = 1; p < plan.n_pass; ++p) {
+    const int R = plan.radix[p], Ns = plan.ns[p];
+    for (int r = 1; r < R; ++r)
+      for (int k = 0; k < Ns; ++k) {
+        double a = -2.0 * kPi * (double)r * (double)k / ((double)Ns * (double)R);
+        t[plan.tw_off[p] + (r - 1) * Ns + k].x = (T)std::cos(a);
+        t[plan.tw_off[p] + (r - 1) * Ns + k].y = (T)std::sin(a);
+      }
   }
   return t;
 }

@@ -29,7 +29,7 @@ int emu_logmel_energy(const roar_sup_config* cfg, const float* audio, int64_t L,
   std::vector<float> win = make_window(*cfg);
   std::vector<float> fb = make_mel_filterbank(*cfg);
   MelRows mr = make_mel_rows(fb, g.n_mels, g.n_bins);
-  std::vector<cf32> tw = make_twiddles<cf32, float>(g.M, g.M);
+  std::vector<cf32> tw = make_pass_twiddles<cf32, float>(g.M);
   std::vector<cf32> twp = make_twiddles<cf32, float>(g.n_fft, g.M + 1);
   const int NT = 256;
   StftParams p;
@@ -67,7 +67,8 @@ int emu_logmel_energy(const roar_sup_config* cfg, const float* audio, int64_t L,
       int Ns = plan.radix[0];
       const cf32* src = s.bufA; cf32* dst = s.bufB;
       for (int ps = 1; ps < plan.n_pass; ++ps) {
-        for (int tid = 0; tid < NT; ++tid) stft_pass_any(plan.radix[ps], p, t, s, gi, tid, Ns, src, dst);
+        for (int tid = 0; tid < NT; ++tid)
+          stft_pass_any(plan.radix[ps], p, t, s, gi, tid, Ns, p.tw + plan.tw_off[ps], src, dst);
         Ns *= plan.radix[ps];
         const cf32* tmp = src; src = dst; dst = const_cast<cf32*>(tmp);
       }
@@ -88,6 +89,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
   Geometry g = geometry(*cfg);
   PyinTables tb = make_pyin_tables(*cfg, g);
   std::vector<cf64> tw = make_twiddles<cf64, double>(g.pf, g.pf);
+  std::vector<cf64> twf = make_pass_twiddles<cf64, double>(g.pf), twh = make_pass_twiddles<cf64, double>(g.pf / 2);
   const int NT = 256;
   PyinParams p;
   memset(&p, 0, sizeof(p));
@@ -98,7 +100,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
   p.span = (p.FT - 1) * g.ph + g.pf;
   p.npb = g.npb; p.nbps = g.nbps; p.kmax = g.kmax; p.n_thr = g.n_thr;
   p.sr = cfg->sample_rate; p.fmin = cfg->pitch_fmin; p.no_trough_prob = cfg->no_trough_prob;
-  p.tw = tw.data(); p.thresholds = tb.thresholds.data(); p.beta_probs = tb.beta_probs.data();
+  p.tw = tw.data(); p.tw_f = twf.data(); p.tw_h = twh.data(); p.thresholds = tb.thresholds.data(); p.beta_probs = tb.beta_probs.data();
   p.beta_cum = tb.beta_cum.data(); p.boltz_exp = tb.boltz_exp.data(); p.boltz_fact = tb.boltz_fact.data();
   const int64_t T = 1 + L / g.ph;
   int64_t sample_off[1] = {0}; int32_t sample_len[1] = {(int32_t)L};
@@ -116,6 +118,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
   std::vector<unsigned char> smem(cmnd_smem_carve(p, nullptr, nullptr) + 64);
   std::vector<cf64> regs((size_t)NT * 8);
   const FftPlan planF = make_plan(p.F), planH = make_plan(p.H);
+  const size_t FP = (size_t)pidx(p.F);
   for (int tile = 0; tile < n_tiles; ++tile) {
     CmndSmem s;
     cmnd_smem_carve(p, smem.data(), &s);
@@ -131,15 +134,15 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
         const int R = planF.radix[ps];
         for (int tid = 0; tid < NT; ++tid) {
           cf64* r = regs.data() + (size_t)tid * 8;
-          if (R == 8) cmnd_pass_compute<8, false>(p, t, s, gi, tid, p.F, Ns, 1, s.buf, p.F, r);
-          else if (R == 4) cmnd_pass_compute<4, false>(p, t, s, gi, tid, p.F, Ns, 1, s.buf, p.F, r);
-          else cmnd_pass_compute<2, false>(p, t, s, gi, tid, p.F, Ns, 1, s.buf, p.F, r);
+          if (R == 8) cmnd_pass_compute<8, false>(p, t, s, gi, tid, p.F, Ns, p.tw_f + planF.tw_off[ps], s.buf, FP, r);
+          else if (R == 4) cmnd_pass_compute<4, false>(p, t, s, gi, tid, p.F, Ns, p.tw_f + planF.tw_off[ps], s.buf, FP, r);
+          else cmnd_pass_compute<2, false>(p, t, s, gi, tid, p.F, Ns, p.tw_f + planF.tw_off[ps], s.buf, FP, r);
         }
         for (int tid = 0; tid < NT; ++tid) {
           const cf64* r = regs.data() + (size_t)tid * 8;
-          if (R == 8) cmnd_pass_store<8>(p, t, gi, tid, p.F, Ns, s.buf, p.F, r);
-          else if (R == 4) cmnd_pass_store<4>(p, t, gi, tid, p.F, Ns, s.buf, p.F, r);
-          else cmnd_pass_store<2>(p, t, gi, tid, p.F, Ns, s.buf, p.F, r);
+          if (R == 8) cmnd_pass_store<8>(p, t, gi, tid, p.F, Ns, s.buf, FP, r);
+          else if (R == 4) cmnd_pass_store<4>(p, t, gi, tid, p.F, Ns, s.buf, FP, r);
+          else cmnd_pass_store<2>(p, t, gi, tid, p.F, Ns, s.buf, FP, r);
         }
         Ns *= R;
       }
@@ -150,15 +153,15 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
         const int R = planH.radix[ps];
         for (int tid = 0; tid < NT; ++tid) {
           cf64* r = regs.data() + (size_t)tid * 8;
-          if (R == 8) cmnd_pass_compute<8, true>(p, t, s, gi, tid, p.H, Ns, 2, s.buf, p.F, r);
-          else if (R == 4) cmnd_pass_compute<4, true>(p, t, s, gi, tid, p.H, Ns, 2, s.buf, p.F, r);
-          else cmnd_pass_compute<2, true>(p, t, s, gi, tid, p.H, Ns, 2, s.buf, p.F, r);
+          if (R == 8) cmnd_pass_compute<8, true>(p, t, s, gi, tid, p.H, Ns, p.tw_h + planH.tw_off[ps], s.buf, FP, r);
+          else if (R == 4) cmnd_pass_compute<4, true>(p, t, s, gi, tid, p.H, Ns, p.tw_h + planH.tw_off[ps], s.buf, FP, r);
+          else cmnd_pass_compute<2, true>(p, t, s, gi, tid, p.H, Ns, p.tw_h + planH.tw_off[ps], s.buf, FP, r);
         }
         for (int tid = 0; tid < NT; ++tid) {
           const cf64* r = regs.data() + (size_t)tid * 8;
-          if (R == 8) cmnd_pass_store<8>(p, t, gi, tid, p.H, Ns, s.buf, p.F, r);
-          else if (R == 4) cmnd_pass_store<4>(p, t, gi, tid, p.H, Ns, s.buf, p.F, r);
-          else cmnd_pass_store<2>(p, t, gi, tid, p.H, Ns, s.buf, p.F, r);
+          if (R == 8) cmnd_pass_store<8>(p, t, gi, tid, p.H, Ns, s.buf, FP, r);
+          else if (R == 4) cmnd_pass_store<4>(p, t, gi, tid, p.H, Ns, s.buf, FP, r);
+          else cmnd_pass_store<2>(p, t, gi, tid, p.H, Ns, s.buf, FP, r);
         }
         Ns *= R;
       }
@@ -180,8 +183,19 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
       for (int l = 0; l < 32; ++l) prob_phase2(p, s, l);
       for (int l = 0; l < 32; ++l) prob_phase3(p, s, l, tb.thresholds.data());
       for (int l = 0; l < 32; ++l) prob_phase4(p, s, l);
-      for (int l = 0; l < 32; ++l) prob_phase5(p, s, l);
-      for (int l = 0; l < 32; ++l) prob_phase6(p, s, fr, l);
+      for (int l = 0; l < 32; ++l) prob_phase5a(p, s, l);
+      for (int c = 0; c < p.n_thr; ++c) s.carry[c] = 0;
+      {
+        const int R = s.cnt[32];
+        for (int base = 0; base < R; base += 32) {
+          int chunk_cr[32];
+          for (int l = 0; l < 32; ++l) chunk_cr[l] = base + l < R ? (int)s.cr[base + l] : 0x7fff;
+          for (int l = 0; l < 32; ++l) prob_phase5b_lane(p, s, base, l, chunk_cr);
+          for (int l = 0; l < 32; ++l) if (chunk_cr[l] < p.n_thr) s.carry[chunk_cr[l]] += 1;
+        }
+      }
+      for (int l = 0; l < 32; ++l) prob_phase6a(p, s, l);
+      for (int l = 0; l < 32; ++l) prob_phase6b(p, s, fr, l);
     }
   }
   // ---- K3 (same per-bin step function; the block argmax is a plain scan here)
@@ -193,6 +207,8 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
   std::vector<cf64> V(2 * (size_t)npb);
   std::vector<double> lpv(npb, tb.lt0);
   std::vector<uint16_t> ptr((size_t)T * 2 * npb);
+  std::vector<int32_t> row_ofs(npb);
+  for (int i = 0; i < npb; ++i) row_ofs[i] = (int32_t)tb.row_id[i] * g.tw;
   auto argmax = [&](const cf64* Vc, int* k, double* m) {
     double best = -1e308; int bk = 0x7fffffff;
     for (int b = 0; b < 2; ++b)
@@ -212,7 +228,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     argmax(Vc, &kstar, &vmax);
     for (int c = 0; c < n_cand[t]; ++c) lpv[cand_bin[(size_t)t * g.kmax + c]] = cand_lp[(size_t)t * g.kmax + c];
     for (int j = 0; j < npb; ++j)
-      vit_step_bin(v, j, Vc, tb.lt_rows.data(), tb.row_id.data(), lpv[j], lp_unv[t], kstar, vmax, &Vn[j],
+      vit_step_bin(v, j, Vc, tb.lt_rows.data(), row_ofs.data(), lpv[j], lp_unv[t], kstar, vmax, &Vn[j],
                    ptr.data() + (size_t)t * 2 * npb);
     for (int c = 0; c < n_cand[t]; ++c) lpv[cand_bin[(size_t)t * g.kmax + c]] = tb.lt0;
   }
