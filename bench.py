@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 KERNEL_NAMES = ["tile_offsets", "stft_mel", "pyin_cmnd", "pyin_probs", "len_sort", "viterbi", "backtrack",
-                "prior", "stats", "fbank_norm"]
+                "prior", "stats", "fbank_norm", "pyin_energy"]
 SR, HOP, N_MELS = 22050, 256, 80
 WORKLOAD = "C2: LJSpeech-shaped 24 h synthetic manifest, 22.05 kHz, n_fft 1024/hop 256/80 mels"
 
@@ -230,8 +230,8 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     launches = ex.kernel_launches - launches0
-    kms = (ctypes.c_double * 10)()
-    kcnt = (ctypes.c_int64 * 10)()
+    kms = (ctypes.c_double * 11)()
+    kcnt = (ctypes.c_int64 * 11)()
     ex.lib.roar_sup_profile_read(ex._h, kms, kcnt, 1)
     ex.lib.roar_sup_set_profiling(ex._h, 0)
     pstats = finalize_pitch_stats(final)
@@ -324,6 +324,7 @@ def main():
     # scratch excluded) -- DESIGN.md section 4
     alg = {
         "stft_mel": 4 * samples + 4 * (N_MELS + 1) * frames,
+        "pyin_energy": 4 * samples,
         "pyin_cmnd": 4 * samples,
         "pyin_probs": 4 * frames,
         "viterbi": 0,
@@ -331,13 +332,15 @@ def main():
         "prior": 4 * prior_elems,
         "stats": 4 * frames,
     }
-    dom = max(("stft_mel", "pyin_cmnd", "pyin_probs", "viterbi", "backtrack", "prior"), key=lambda k: per[k])
+    dom = max(("stft_mel", "pyin_energy", "pyin_cmnd", "pyin_probs", "viterbi", "backtrack", "prior"),
+              key=lambda k: per[k])
     # the pYIN chain is one logical kernel split at two scratch hand-offs: its algorithmic traffic is
     # the audio in (4*hop B/frame) and f0 / flag / prob out (12 B/frame)
     pyin_alg = 4 * samples + 12 * frames
-    if dom in ("pyin_cmnd", "pyin_probs", "viterbi", "backtrack"):
-        dom_alg, dom_ms = pyin_alg, per["pyin_cmnd"] + per["pyin_probs"] + per["viterbi"] + per["backtrack"]
-        dom_name = "pyin chain (pyin_cmnd + pyin_probs + viterbi + backtrack); slowest member: " + dom
+    if dom in ("pyin_energy", "pyin_cmnd", "pyin_probs", "viterbi", "backtrack"):
+        dom_alg = pyin_alg
+        dom_ms = per["pyin_energy"] + per["pyin_cmnd"] + per["pyin_probs"] + per["viterbi"] + per["backtrack"]
+        dom_name = "pyin chain (pyin_energy + pyin_cmnd + pyin_probs + viterbi + backtrack); slowest member: " + dom
     else:
         dom_alg, dom_ms, dom_name = alg[dom], per[dom], dom
     n_launch = max(1, len(bounds))

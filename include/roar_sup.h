@@ -92,7 +92,7 @@ typedef struct roar_sup_handle roar_sup_handle;
 /* kernel ids for the optional per-kernel timing below */
 enum roar_sup_kernel { ROAR_K_TILE_OFFSETS = 0, ROAR_K_STFT_MEL = 1, ROAR_K_PYIN_CMND = 2, ROAR_K_PYIN_PROBS = 3,
                        ROAR_K_LEN_SORT = 4, ROAR_K_VITERBI = 5, ROAR_K_BACKTRACK = 6, ROAR_K_PRIOR = 7,
-                       ROAR_K_STATS = 8, ROAR_K_FBANK_NORM = 9, ROAR_K_COUNT = 10 };
+                       ROAR_K_STATS = 8, ROAR_K_FBANK_NORM = 9, ROAR_K_PYIN_ENERGY = 10, ROAR_K_COUNT = 11 };
 
 /* Fill cfg with the reference's extraction defaults
  * (scripts/dataset_processing/tts/rasa/ds_conf/ds_for_fastpitch_align.yaml:12-27). */

@@ -1,10 +1,14 @@
 // K2  pYIN front end.
 //   K2a  pyin_cmnd : per frame, YIN difference function -> cumulative-mean-normalised difference.
-//        The autocorrelation uses the reference's own formulation (float64 FFT of the frame and of
-//        its reversed first half, product, inverse FFT) as ONE packed complex FFT of size F plus one
-//        half-size inverse, in shared memory; the energy terms replay the reference's float32
-//        sequential cumsum bit for bit (it carries ~1e-4 relative noise into the trough heights, so
-//        replaying it is what makes the thresholds agree).
+//        The autocorrelation  acf[tau] = sum_{j=1..W} y[j] * y[j+tau]  (what the reference obtains
+//        through float64 FFTs) is evaluated DIRECTLY in float64: the products of two float32 samples
+//        are exact in float64, so the only rounding is the accumulation.  Consecutive frames overlap
+//        by W - hop samples, so the sum is split into hop-sized blocks Q_m[tau] shared by the W/hop
+//        frames that contain block m (half the work at the default W = 2*hop).  Each thread owns
+//        R = 12 consecutive lags of one block: a register-resident sliding window gives 12 DFMA per
+//        two shared-memory loads.  The energy terms replay the reference's float32 sequential cumsum
+//        bit for bit (it carries ~1e-4 relative noise into the trough heights, so replaying it is
+//        what makes the thresholds agree).
 //   K2b  pyin_probs: per frame (one warp), parabolic shifts, troughs, threshold-beta / Boltzmann
 //        probabilities, pitch-bin quantisation -> sparse observation list + voiced probability.
 //
@@ -12,9 +16,10 @@
 // `__pyin_helper` as called from roar/collections/tts/data/dataset.py:696-703.
 #pragma once
 #include "common.cuh"
-#include "fft.cuh"
 
 namespace roar {
+
+constexpr int ACF_R = 12;   // lags per thread (multiple of 4: keeps the padded smem offsets static)
 
 struct PyinParams {
   const float* audio;
@@ -24,21 +29,23 @@ struct PyinParams {
   const int32_t* tile_off;    // [n_utts+1]
   int32_t n_utts;
   // geometry
-  int32_t F, W, hop, H;       // frame, win, hop, F/2
+  int32_t F, W, hop;          // frame, win, hop
   int32_t min_period, max_period, n_lags;
-  int32_t FT, span, P, G;     // frames per tile, audio span, threads per frame, frames in flight
+  int32_t FT;                 // frames per tile
+  int32_t BL, nb;             // autocorrelation block length, blocks per frame (W = nb*BL when shared)
+  int32_t n_groups;           // ceil((max_period+1) / ACF_R) lag groups
+  int32_t ylen;               // staged samples per tile (incl. zero tail read by the padded lag groups)
   int32_t npb, nbps, kmax, n_thr;
   double sr, fmin, no_trough_prob;
   // tables
-  const cf64* tw;             // [F] W_F^k (float64), read through L1 (inverse packing)
-  const cf64* tw_f;           // per-pass Stockham twiddles, size F (fft.cuh layout)
-  const cf64* tw_h;           // per-pass Stockham twiddles, size F/2
   const double* thresholds;   // [n_thr+1]
   const double* beta_probs;   // [n_thr]
   const double* beta_cum;     // [n_thr+1]
   const double* boltz_exp;    // [kmax+1]
   const double* boltz_fact;   // [kmax+1]
   // scratch / outputs
+  float* energy;              // [max_period+1, total_frames]  E[tau] = cs[W+tau] - cs[tau] (float32 scratch, frame-contiguous)
+  const int32_t* etile_off;   // [n_utts+1] prefix sum of ceil(T_i / 32): energy-kernel tiles
   double* cmnd;               // [total_frames, n_lags]
   uint16_t* cand_bin;         // [total_frames, kmax]
   double* cand_lp;            // [total_frames, kmax]
@@ -48,27 +55,45 @@ struct PyinParams {
   int64_t total_frames;
 };
 
+// autocorrelation blocking: blocks of `hop` samples shared between frames when W is a multiple of
+// hop, one private block of W samples per frame otherwise
+HD void cmnd_blocking(int W, int hop, int* BL, int* nb) {
+  if (W % hop == 0) { *BL = hop; *nb = W / hop; } else { *BL = W; *nb = 1; }
+}
+HD int cmnd_n_blocks(const PyinParams& p, int nf) { return nf + p.nb - 1; }
+// samples of the tile the kernel touches: frames, plus the zero tail the padded lag groups read
+HD int cmnd_ylen(int FT, int F, int hop, int BL, int nb, int n_groups) {
+  const int a = (FT - 1) * hop + F;
+  const int b = (FT + nb - 2) * hop + BL + n_groups * ACF_R + 1;
+  return ((a > b ? a : b) + 3) & ~3;
+}
+// one pad double per 4: a lane stride of ACF_R = 12 samples becomes 15 doubles -> conflict-free
+HD int ypad(int i) { return i + (i >> 2); }
+
 struct CmndSmem {
-  float* audio;    // [span]
-  cf64* buf;       // [G][pidx(F)]
-  float* E;        // [FT][max_period+1]
-  double* d;       // [G][max_period+1]   difference function, then chunk-local prefix sums
-  double* dsum;    // [G][max_period+1]
-  double* chunk;   // [G][32] chunk totals, [G][32] chunk offsets
+  double* yd;      // [ypad(ylen)]   tile samples as float64 (exact), zero outside the utterance
+  double* Q;       // [FT+nb-1][QS]  block partial autocorrelations; then d[f][tau] in place
+  float* E;        // [max_period+1][FT]  the tile's energy terms (from K2a-0's scratch)
+  // aliases of yd, valid once the autocorrelation is done
+  double* dsum;    // [n_slots][max_period+1]
+  double* chunk;   // [n_slots][64]
 };
 
 HD size_t cmnd_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+HD int cmnd_qs(const PyinParams& p) { return p.n_groups * ACF_R; }
+constexpr int CMND_SLOTS = 8;   // frames scanned concurrently (one warp each)
 
 HD size_t cmnd_smem_carve(const PyinParams& p, unsigned char* base, CmndSmem* s) {
   size_t o = 0;
 #define CARVE(field, type, count) { if (s) s->field = (type*)(base + o); o = cmnd_align16(o + sizeof(type) * (size_t)(count)); }
-  CARVE(buf, cf64, (size_t)p.G * pidx(p.F) + 8)
-  CARVE(d, double, (size_t)p.G * (p.max_period + 1))
-  CARVE(dsum, double, (size_t)p.G * (p.max_period + 1))
-  CARVE(chunk, double, (size_t)p.G * 64)
-  CARVE(audio, float, p.span)
+  size_t ny = (size_t)ypad(p.ylen) + 4;
+  const size_t alias = (size_t)CMND_SLOTS * (p.max_period + 1) + (size_t)CMND_SLOTS * 64;
+  if (ny < alias) ny = alias;
+  CARVE(yd, double, ny)
+  CARVE(Q, double, (size_t)(p.FT + p.nb - 1) * cmnd_qs(p))
   CARVE(E, float, (size_t)p.FT * (p.max_period + 1))
 #undef CARVE
+  if (s) { s->dsum = s->yd; s->chunk = s->yd + (size_t)CMND_SLOTS * (p.max_period + 1); }
   return o;
 }
 
@@ -96,192 +121,167 @@ HD bool pyin_locate(const PyinParams& p, int tile, PyinTile* t) {
 }
 
 HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int tid, int nthr) {
-  const int n = (t.nf - 1) * p.hop + p.F;
-  for (int i = tid; i < n; i += nthr) {
+  // energy terms first: asynchronous 4-byte copies on the device, consumed after the autocorrelation
+  const float* Eg = p.energy + (p.frame_off[t.utt] + t.t0);
+  const int ne = (p.max_period + 1) * t.nf;
+  for (int i = tid; i < ne; i += nthr) {
+    const int tau = i / t.nf, f = i - tau * t.nf;
+    const float* src = Eg + (size_t)tau * p.total_frames + f;
+    float* dst = s.E + tau * p.FT + f;
+#if defined(__CUDA_ARCH__)
+    const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d32), "l"(src) : "memory");
+#else
+    *dst = *src;
+#endif
+  }
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+  for (int i = tid; i < p.ylen; i += nthr) {
     const int64_t q = t.p0 + i;
-    s.audio[i] = (q >= 0 && q < t.L) ? p.audio[t.off + q] : 0.f;
+    s.yd[ypad(i)] = (q >= 0 && q < t.L) ? (double)p.audio[t.off + q] : 0.0;
   }
 }
 
-// float32 sequential cumsum of y^2 (np.cumsum(y_frames**2, axis=-2) on float32 frames), one thread
-// per frame; keeps only what the difference function needs: E[tau] = cs[W+tau] - cs[tau].
-// The frames of a tile are spread over warps (lane 0/1 of each) so the strided reads do not pile
-// onto one bank.
-HD float f32_sq_add(float cs, float y) {
+// K2a-0  float32 sequential cumsum of y^2 (np.cumsum(y_frames**2, axis=-2) on float32 frames): an
+// inherently serial chain per frame, so it runs as its own small kernel -- one warp per tile of 32
+// consecutive frames, one lane per frame, the tile's squared samples staged in shared memory -- instead
+// of stalling a tile of K2a.  E[tau] = cs[W+tau] - cs[tau] (|.| < 1e-6 flushed to 0 like the reference):
+// cs[tau] is not parked anywhere, a second accumulator replays the same additions tau = 0..max_period
+// in lockstep (bit-identical by construction), so the chain never waits on memory it wrote itself.
+HD float f32_mul(float a, float b) {
 #if defined(__CUDA_ARCH__)
-  return __fadd_rn(cs, __fmul_rn(y, y));
+  return __fmul_rn(a, b);
 #else
-  volatile float sq = y * y;
-  volatile float r = cs + sq;
-  return r;
+  volatile float r = a * b; return r;
 #endif
 }
-HD void cmnd_phase_energy(const PyinParams& p, const PyinTile& t, CmndSmem& s, int tid, int nthr) {
-  const int nwarp = nthr / 32 > 0 ? nthr / 32 : 1;
-  const int warp = tid / 32, lane = tid % 32;
-  const int f = lane * nwarp + warp;
-  if (lane >= (p.FT + nwarp - 1) / nwarp || f >= t.nf) return;
-  const float* y = s.audio + f * p.hop;
-  float* E = s.E + (size_t)f * (p.max_period + 1);
-  // three straight loops (no load/store aliasing inside a loop, so the loads pipeline):
-  //   A: cs[n] for n <= max_period, kept in E;  B: keep accumulating up to W-1;
-  //   C: n = W + tau: E[tau] = cs[W+tau] - cs[tau]
-  float cs = 0.f;
-  int n = 0;
-  for (; n <= p.max_period && n < p.W; ++n) { cs = f32_sq_add(cs, y[n]); E[n] = cs; }
-  for (; n < p.W; ++n) cs = f32_sq_add(cs, y[n]);
+HD float f32_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b; return r;
+#endif
+}
+HD float f32_sub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  volatile float r = a - b; return r;
+#endif
+}
+constexpr int ENERGY_FT = 32;   // frames per energy tile (one warp)
+HD int epad(int i, int hop) { return i + i / hop; }   // frame stride hop+1 floats: conflict-free lanes
+HD int energy_span(const PyinParams& p) { return (ENERGY_FT - 1) * p.hop + p.W + p.max_period + 1; }
+// stage the tile's squared samples (zero outside the utterance; librosa center=True, pad_mode="constant")
+HD void pyin_energy_stage(const PyinParams& p, const float* y, int L, int64_t q0, int n, float* sq, int tid,
+                          int nthr) {
+  for (int i = tid; i < n; i += nthr) {
+    const int64_t q = q0 + i;
+    const float v = (q >= 0 && q < L) ? y[q] : 0.f;
+    sq[epad(i, p.hop)] = f32_mul(v, v);
+  }
+}
+// walks the epad layout sample by sample without dividing: `left` samples remain before the pad slot
+struct EpadWalk {
+  const float* p; int left, hop;
+  HD EpadWalk(const float* sq, int i, int hop_) : p(sq + epad(i, hop_)), left(hop_ - i % hop_), hop(hop_) {}
+  HD float next() {
+    const float v = *p++;
+    if (--left == 0) { ++p; left = hop; }
+    return v;
+  }
+};
+// one frame's chain; E = &energy[frame], rows `stride` floats apart (frame-contiguous rows)
+HD void pyin_energy_frame(const PyinParams& p, const float* sq, int f, float* E, size_t stride) {
+  const int base = f * p.hop;
+  float cs = 0.f, cs2 = 0.f;
+  EpadWalk hi(sq, base, p.hop), lo(sq, base, p.hop);
+  for (int n = 0; n < p.W; ++n) cs = f32_add(cs, hi.next());
   for (int tau = 0; tau <= p.max_period; ++tau) {
-    cs = f32_sq_add(cs, y[p.W + tau]);
-    if (p.W + tau <= p.max_period) {   // only when max_period >= W (non-default win_length)
-      const float keep = cs;
-      const float lo0 = E[tau];
-      E[p.W + tau] = keep;
-      float e0 = cs - lo0;
-      if (fabsf(e0) < 1e-6f) e0 = 0.f;
-      E[tau] = e0;
-      continue;
-    }
-#if defined(__CUDA_ARCH__)
-    float e = __fsub_rn(cs, E[tau]);
-#else
-    float e = cs - E[tau];
-#endif
+    cs = f32_add(cs, hi.next());
+    cs2 = f32_add(cs2, lo.next());
+    float e = f32_sub(cs, cs2);
     if (fabsf(e) < 1e-6f) e = 0.f;
-    E[tau] = e;
+    *E = e;
+    E += stride;
   }
 }
 
-// first radix-8 pass of the packed FFT: z[n] = y[n] + i * yrev[n], yrev[k] = y[W-k] (k < W), 0 after
-HD void cmnd_first_pass(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid) {
-  const int slot = tid / p.P, u = tid - slot * p.P;
-  const int f = g * p.G + slot;
-  if (f >= t.nf) return;
-  const float* y = s.audio + f * p.hop;
-  cf64* out = s.buf + (size_t)slot * pidx(p.F);
-  const int nb = p.F / 8;
-  for (int j = u; j < nb; j += p.P) {
-    cf64 v[8];
+// Autocorrelation work is handed out in warp-sized chunks: chunk c = (block m, part) where a block's
+// lag groups are split into `cpb` parts of at most 32 lanes, so all lanes of a warp share the block
+// (one broadcast load for y[j]) and read windows 15 doubles apart (conflict-free).
+HD int cmnd_cpb(const PyinParams& p) { return (p.n_groups + 31) / 32; }
+HD int cmnd_lpc(const PyinParams& p) { const int c = cmnd_cpb(p); return (p.n_groups + c - 1) / c; }
+
+// One autocorrelation unit: block m, lag group g ->  Q[m][tau] = sum_{j=1..BL} y[m*hop+j] * y[m*hop+j+tau]
+// for tau = g*R .. g*R+R-1.  The window y[j+tau0 .. j+tau0+R-1] lives in registers and slides by one
+// sample per step (static rotation: the loop is unrolled by R).  m*hop and g*R are multiples of 4,
+// so every padded shared-memory offset inside the unrolled body is a compile-time constant.
+HD void cmnd_acf_unit(const PyinParams& p, CmndSmem& s, int m, int g) {
+  constexpr int R = ACF_R;
+  const int b0 = m * p.hop;                // j = 1..BL -> samples b0+1 .. b0+BL
+  const double* ya = s.yd + ypad(b0);
+  const double* yw = s.yd + ypad(b0 + g * R);
+  double acc[R], win[R];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int n = j + r * nb;
-      v[r].x = (double)y[n];
-      v[r].y = n < p.W ? (double)y[p.W - n] : 0.0;
-    }
-    dft8<false>(v);
-    stockham_store<8>(v, out, 1, j);
-  }
-}
-
-// in-place pass: load+compute into registers (phase a), barrier, store (phase b).
-// Each thread owns at most 8/R butterflies (M/P <= 8), fully unrolled so `regs` stays in registers.
-template <int R, bool INV>
-HD void cmnd_pass_compute(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid, int M,
-                          int Ns, const cf64* twp, const cf64* in_base, size_t slot_stride, cf64* regs) {
-  const int slot = tid / p.P, u = tid - slot * p.P;
-  const int f = g * p.G + slot;
-  if (f >= t.nf) return;
-  const cf64* in = in_base + (size_t)slot * slot_stride;
-  const int nb = M / R;
+  for (int r = 0; r < R; ++r) acc[r] = 0.0;
 #pragma unroll
-  for (int q = 0; q < 8 / R; ++q) {
-    const int j = u + q * p.P;
-    if (j < nb) {
-      cf64* v = regs + q * R;
-      stockham_load<R>(v, in, M, j);
-      stockham_twiddle_dft<R, INV>(v, Ns, j, twp);
-    }
-  }
-}
-template <int R>
-HD void cmnd_pass_store(const PyinParams& p, const PyinTile& t, int g, int tid, int M, int Ns,
-                        cf64* out_base, size_t slot_stride, const cf64* regs) {
-  const int slot = tid / p.P, u = tid - slot * p.P;
-  const int f = g * p.G + slot;
-  if (f >= t.nf) return;
-  cf64* out = out_base + (size_t)slot * slot_stride;
-  const int nb = M / R;
+  for (int r = 0; r < R - 1; ++r) win[r] = yw[(r + 1) + ((r + 1) >> 2)];
+  const int full = p.BL / R * R;
+  int jj = 0;
+  for (; jj < full; jj += R) {
+    const double* a_ = ya + jj + (jj >> 2);
+    const double* w_ = yw + jj + (jj >> 2);
 #pragma unroll
-  for (int q = 0; q < 8 / R; ++q) {
-    const int j = u + q * p.P;
-    if (j < nb) stockham_store<R>(regs + q * R, out, Ns, j);
+    for (int st = 0; st < R; ++st) {
+      const double a = a_[(st + 1) + ((st + 1) >> 2)];
+      win[(st + R - 1) % R] = w_[(st + R) + ((st + R) >> 2)];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fma(a, win[(st + r) % R], acc[r]);
+    }
   }
+  {   // tail (BL not a multiple of R): same body, guarded
+    const double* a_ = ya + jj + (jj >> 2);
+    const double* w_ = yw + jj + (jj >> 2);
+#pragma unroll
+    for (int st = 0; st < R; ++st) {
+      if (jj + st < p.BL) {
+        const double a = a_[(st + 1) + ((st + 1) >> 2)];
+        win[(st + R - 1) % R] = w_[(st + R) + ((st + R) >> 2)];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fma(a, win[(st + r) % R], acc[r]);
+      }
+    }
+  }
+  double* q = s.Q + (size_t)m * cmnd_qs(p) + g * R;
+#pragma unroll
+  for (int r = 0; r < R; ++r) q[r] = acc[r];
 }
 
-// spectra of the two real sequences from the packed transform, their product, and the packing of
-// the half-size inverse:  C[k] = A[k]*B[k];  Zr[k] = (C[k]+conj(C[H-k])) + i e^{+2 pi i k/F} (C[k]-conj(C[H-k]))
-HD void cmnd_phase_product(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid) {
-  const int slot = tid / p.P, u = tid - slot * p.P;
-  const int f = g * p.G + slot;
-  if (f >= t.nf) return;
-  cf64* Z = s.buf + (size_t)slot * pidx(p.F);
-  for (int k = u; k <= p.H; k += p.P) {
-    const cf64 zk = Z[pidx(k)];
-    const cf64 zc = cconj(Z[pidx((p.F - k) & (p.F - 1))]);
-    cf64 A, B;
-    A.x = 0.5 * (zk.x + zc.x); A.y = 0.5 * (zk.y + zc.y);
-    B.x = 0.5 * (zk.y - zc.y); B.y = -0.5 * (zk.x - zc.x);   // (zk - zc)/(2i)
-    Z[pidx(k)] = cmul(A, B);
-  }
-}
-HD void cmnd_phase_pack_inverse(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid) {
-  const int slot = tid / p.P, u = tid - slot * p.P;
-  const int f = g * p.G + slot;
-  if (f >= t.nf) return;
-  cf64* C = s.buf + (size_t)slot * pidx(p.F);
-  for (int k = u; k <= p.H / 2; k += p.P) {
-    const int k2 = p.H - k;
-    const cf64 ck = C[pidx(k)], c2 = C[pidx(k2)];
-    // k
-    {
-      cf64 a = cadd(ck, cconj(c2)), b = csub(ck, cconj(c2));
-      cf64 w = ld_ro(p.tw + k); w.y = -w.y;          // e^{+2 pi i k / F}
-      cf64 wb = cmul(w, b);
-      cf64 r; r.x = a.x - wb.y; r.y = a.y + wb.x;    // a + i*wb
-      C[pidx(k)] = r;
-    }
-    if (k2 != k && k2 < p.H) {
-      cf64 a = cadd(c2, cconj(ck)), b = csub(c2, cconj(ck));
-      cf64 w = ld_ro(p.tw + k2); w.y = -w.y;
-      cf64 wb = cmul(w, b);
-      cf64 r; r.x = a.x - wb.y; r.y = a.y + wb.x;
-      C[pidx(k2)] = r;
+// difference function d[tau] = (E[0] + E[tau]) - 2*acf[tau], acf = sum of the frame's blocks, written
+// in place over Q[f]; one thread per lag walks the frames in order (Q[f+1..] is still intact).
+HD void cmnd_phase_diff(const PyinParams& p, const PyinTile& t, CmndSmem& s, int tid, int nthr) {
+  const int qs = cmnd_qs(p);
+  for (int tau = tid; tau <= p.max_period; tau += nthr) {
+    for (int f = 0; f < t.nf; ++f) {
+      double acf = s.Q[(size_t)f * qs + tau];
+      for (int b = 1; b < p.nb; ++b) acf += s.Q[(size_t)(f + b) * qs + tau];
+      if (fabs(acf) < 1e-6) acf = 0.0;
+      const float e2 = f32_add(s.E[f], s.E[tau * p.FT + f]);
+      s.Q[(size_t)f * qs + tau] = (double)e2 - 2.0 * acf;
     }
   }
 }
 
-// difference function from the inverse transform (real sequence r[m] = interleaved re/im of z2)
-HD void cmnd_phase_diff(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid,
-                        const cf64* z2_base) {
-  const int slot = tid / p.P, u = tid - slot * p.P;
-  const int f = g * p.G + slot;
-  if (f >= t.nf) return;
-  const cf64* z2 = z2_base + (size_t)slot * pidx(p.F);
-  const float* E = s.E + (size_t)f * (p.max_period + 1);
-  double* d = s.d + (size_t)slot * (p.max_period + 1);
-  const double scale = 1.0 / p.F;
-  for (int tau = u; tau <= p.max_period; tau += p.P) {
-    const int m = p.W + tau;
-    const cf64 zz = z2[pidx(m >> 1)];
-    double acf = ((m & 1) ? zz.y : zz.x) * scale;
-    if (fabs(acf) < 1e-6) acf = 0.0;
-#if defined(__CUDA_ARCH__)
-    const float e2 = __fadd_rn(E[0], E[tau]);
-#else
-    volatile float e2v = E[0] + E[tau]; const float e2 = e2v;
-#endif
-    d[tau] = (double)e2 - 2.0 * acf;
-  }
-}
-
-// cumulative sum of d[1..max_period] in three steps (chunk-local prefix, chunk offsets, combine)
+// cumulative sum of d[1..max_period] per frame: chunk-local prefix, chunk offsets, combine.
+// One 32-lane slot per frame.
 HD int cmnd_chunk(const PyinParams& p) { return (p.max_period + 31) / 32; }
 
-HD void cmnd_phase_scan1(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid) {
-  const int slot = tid / p.P, u = tid - slot * p.P;
-  const int f = g * p.G + slot;
-  if (f >= t.nf || u >= 32) return;
+HD void cmnd_phase_scan1(const PyinParams& p, CmndSmem& s, int f, int slot, int u) {
   const int ch = cmnd_chunk(p);
-  const double* d = s.d + (size_t)slot * (p.max_period + 1);
+  const double* d = s.Q + (size_t)f * cmnd_qs(p);
   double* ds = s.dsum + (size_t)slot * (p.max_period + 1);
   double acc = 0.0;
   for (int i = 0; i < ch; ++i) {
@@ -290,29 +290,21 @@ HD void cmnd_phase_scan1(const PyinParams& p, const PyinTile& t, CmndSmem& s, in
     acc += d[tau];
     ds[tau] = acc;
   }
-  s.chunk[slot * 32 + u] = acc;
+  s.chunk[slot * 64 + u] = acc;
 }
-HD void cmnd_phase_scan2(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid,
-                         double* offs /* [G][32] */) {
-  const int slot = tid / p.P, u = tid - slot * p.P;
-  const int f = g * p.G + slot;
-  if (f >= t.nf || u >= 32) return;
+HD void cmnd_phase_scan2(const PyinParams& p, CmndSmem& s, int slot, int u) {
   double acc = 0.0;
-  for (int v = 0; v < u; ++v) acc += s.chunk[slot * 32 + v];
-  offs[slot * 32 + u] = acc;
+  for (int v = 0; v < u; ++v) acc += s.chunk[slot * 64 + v];
+  s.chunk[slot * 64 + 32 + u] = acc;
 }
-HD void cmnd_phase_emit(const PyinParams& p, const PyinTile& t, CmndSmem& s, int g, int tid,
-                        const double* offs) {
-  const int slot = tid / p.P, u = tid - slot * p.P;
-  const int f = g * p.G + slot;
-  if (f >= t.nf) return;
+HD void cmnd_phase_emit(const PyinParams& p, const PyinTile& t, CmndSmem& s, int f, int slot, int u) {
   const int ch = cmnd_chunk(p);
-  const double* d = s.d + (size_t)slot * (p.max_period + 1);
+  const double* d = s.Q + (size_t)f * cmnd_qs(p);
   const double* ds = s.dsum + (size_t)slot * (p.max_period + 1);
   double* out = p.cmnd + (size_t)(p.frame_off[t.utt] + t.t0 + f) * p.n_lags;
-  for (int i = u; i < p.n_lags; i += p.P) {
+  for (int i = u; i < p.n_lags; i += 32) {
     const int tau = p.min_period + i;
-    const double c = ds[tau] + offs[slot * 32 + (tau - 1) / ch];
+    const double c = ds[tau] + s.chunk[slot * 64 + 32 + (tau - 1) / ch];
     out[i] = d[tau] / (c / (double)tau + 2.2250738585072014e-308);
   }
 }
@@ -507,66 +499,56 @@ HD void prob_phase6b(const PyinParams& p, ProbSmem& s, int64_t frame, int lane) 
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(256) k_pyin_cmnd(const PyinParams p) {
+// one warp per tile of 32 consecutive frames of one utterance, one lane per frame
+__global__ void __launch_bounds__(32) k_pyin_energy(const PyinParams p) {
+  extern __shared__ __align__(16) float e_smem[];
+  const int tile = blockIdx.x, lane = threadIdx.x;
+  if (tile >= p.etile_off[p.n_utts]) return;
+  int lo = 0, hi = p.n_utts;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (p.etile_off[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const int T = (int)(p.frame_off[lo + 1] - p.frame_off[lo]);
+  const int t0 = (tile - p.etile_off[lo]) * ENERGY_FT;
+  const int nf = T - t0 < ENERGY_FT ? T - t0 : ENERGY_FT;
+  const int n = (nf - 1) * p.hop + p.W + p.max_period + 1;
+  pyin_energy_stage(p, p.audio + p.sample_off[lo], p.sample_len[lo], (int64_t)t0 * p.hop - p.F / 2, n, e_smem,
+                    lane, 32);
+  __syncwarp();
+  if (lane < nf)
+    pyin_energy_frame(p, e_smem, lane, p.energy + (p.frame_off[lo] + t0 + lane), (size_t)p.total_frames);
+}
+
+constexpr int CMND_THREADS = 256;   // 8 warps, each takes every 8th autocorrelation chunk
+__global__ void __launch_bounds__(CMND_THREADS, 2) k_pyin_cmnd(const PyinParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   CmndSmem s;
   cmnd_smem_carve(p, smem_raw, &s);
-  const int nthr = blockDim.x, tid = threadIdx.x;
+  const int nthr = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   PyinTile t;
   if (!pyin_locate(p, blockIdx.x, &t)) return;
   cmnd_phase_load(p, t, s, tid, nthr);
   __syncthreads();
-  cmnd_phase_energy(p, t, s, tid, nthr);
+  {
+    const int cpb = cmnd_cpb(p), lpc = cmnd_lpc(p);
+    const int n_chunks = cmnd_n_blocks(p, t.nf) * cpb;
+    for (int c = warp; c < n_chunks; c += CMND_SLOTS) {
+      const int m = c / cpb, g = (c - m * cpb) * lpc + lane;
+      if (lane < lpc && g < p.n_groups) cmnd_acf_unit(p, s, m, g);
+    }
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncthreads();
-  const FftPlan planF = make_plan(p.F);
-  const FftPlan planH = make_plan(p.H);
-  const size_t FP = (size_t)pidx(p.F);
-  cf64 regs[8];
-  const int n_groups = (t.nf + p.G - 1) / p.G;
-  for (int g = 0; g < n_groups; ++g) {
-    cmnd_first_pass(p, t, s, g, tid);
-    __syncthreads();
-    int Ns = 8;
-    for (int ps = 1; ps < planF.n_pass; ++ps) {
-      const int R = planF.radix[ps];
-      const cf64* twp = p.tw_f + planF.tw_off[ps];
-      if (R == 8) cmnd_pass_compute<8, false>(p, t, s, g, tid, p.F, Ns, twp, s.buf, FP, regs);
-      else if (R == 4) { cmnd_pass_compute<4, false>(p, t, s, g, tid, p.F, Ns, twp, s.buf, FP, regs); }
-      else { cmnd_pass_compute<2, false>(p, t, s, g, tid, p.F, Ns, twp, s.buf, FP, regs); }
-      __syncthreads();
-      if (R == 8) cmnd_pass_store<8>(p, t, g, tid, p.F, Ns, s.buf, FP, regs);
-      else if (R == 4) cmnd_pass_store<4>(p, t, g, tid, p.F, Ns, s.buf, FP, regs);
-      else cmnd_pass_store<2>(p, t, g, tid, p.F, Ns, s.buf, FP, regs);
-      __syncthreads();
-      Ns *= R;
-    }
-    cmnd_phase_product(p, t, s, g, tid);
-    __syncthreads();
-    cmnd_phase_pack_inverse(p, t, s, g, tid);
-    __syncthreads();
-    // half-size inverse, in place as well (keeps one buffer per frame)
-    Ns = 1;
-    for (int ps = 0; ps < planH.n_pass; ++ps) {
-      const int R = planH.radix[ps];
-      const cf64* twp = p.tw_h + planH.tw_off[ps];
-      if (R == 8) cmnd_pass_compute<8, true>(p, t, s, g, tid, p.H, Ns, twp, s.buf, FP, regs);
-      else if (R == 4) cmnd_pass_compute<4, true>(p, t, s, g, tid, p.H, Ns, twp, s.buf, FP, regs);
-      else cmnd_pass_compute<2, true>(p, t, s, g, tid, p.H, Ns, twp, s.buf, FP, regs);
-      __syncthreads();
-      if (R == 8) cmnd_pass_store<8>(p, t, g, tid, p.H, Ns, s.buf, FP, regs);
-      else if (R == 4) cmnd_pass_store<4>(p, t, g, tid, p.H, Ns, s.buf, FP, regs);
-      else cmnd_pass_store<2>(p, t, g, tid, p.H, Ns, s.buf, FP, regs);
-      __syncthreads();
-      Ns *= R;
-    }
-    cmnd_phase_diff(p, t, s, g, tid, s.buf);
-    __syncthreads();
-    cmnd_phase_scan1(p, t, s, g, tid);
-    __syncthreads();
-    cmnd_phase_scan2(p, t, s, g, tid, s.chunk + (size_t)p.G * 32);
-    __syncthreads();
-    cmnd_phase_emit(p, t, s, g, tid, s.chunk + (size_t)p.G * 32);
-    __syncthreads();
+  cmnd_phase_diff(p, t, s, tid, nthr);
+  __syncthreads();
+  for (int f = warp; f < t.nf; f += CMND_SLOTS) {
+    cmnd_phase_scan1(p, s, f, warp, lane);
+    __syncwarp();
+    cmnd_phase_scan2(p, s, warp, lane);
+    __syncwarp();
+    cmnd_phase_emit(p, t, s, f, warp, lane);
+    __syncwarp();
   }
 }
 

@@ -42,9 +42,8 @@ struct roar_sup_handle {
   int stft_FT = 16, stft_P = 64, stft_G = 4, stft_span = 0; size_t stft_smem = 0;
   int use_tma = 1;
   // K2
-  cf64 *d_tw64 = nullptr, *d_tw64_f = nullptr, *d_tw64_h = nullptr;
   double *d_thr = nullptr, *d_beta = nullptr, *d_beta_cum = nullptr, *d_bexp = nullptr, *d_bfact = nullptr;
-  int pyin_FT = 16, pyin_P = 128, pyin_G = 2, pyin_span = 0; size_t cmnd_smem = 0, prob_smem = 0;
+  int pyin_FT = 15, pyin_BL = 0, pyin_nb = 0, pyin_ngroups = 0, pyin_ylen = 0; size_t cmnd_smem = 0, prob_smem = 0, energy_smem = 0;
   // K3
   double* d_lt_rows = nullptr; uint16_t* d_row_id = nullptr; double* d_freqs = nullptr;
   int n_rows = 0; double lt0 = 0, li_v = 0, li_u = 0;
@@ -115,12 +114,12 @@ static PyinParams pyin_params_base(const roar_sup_handle* h) {
   PyinParams p;
   memset(&p, 0, sizeof(p));
   const Geometry& g = h->g;
-  p.F = g.pf; p.W = g.pw; p.hop = g.ph; p.H = g.pf / 2;
+  p.F = g.pf; p.W = g.pw; p.hop = g.ph;
   p.min_period = g.min_period; p.max_period = g.max_period; p.n_lags = g.n_lags;
-  p.FT = h->pyin_FT; p.span = h->pyin_span; p.P = h->pyin_P; p.G = h->pyin_G;
+  p.FT = h->pyin_FT; p.BL = h->pyin_BL; p.nb = h->pyin_nb; p.n_groups = h->pyin_ngroups; p.ylen = h->pyin_ylen;
   p.npb = g.npb; p.nbps = g.nbps; p.kmax = g.kmax; p.n_thr = g.n_thr;
   p.sr = h->cfg.sample_rate; p.fmin = h->cfg.pitch_fmin; p.no_trough_prob = h->cfg.no_trough_prob;
-  p.tw = h->d_tw64; p.tw_f = h->d_tw64_f; p.tw_h = h->d_tw64_h; p.thresholds = h->d_thr; p.beta_probs = h->d_beta; p.beta_cum = h->d_beta_cum;
+  p.thresholds = h->d_thr; p.beta_probs = h->d_beta; p.beta_cum = h->d_beta_cum;
   p.boltz_exp = h->d_bexp; p.boltz_fact = h->d_bfact;
   return p;
 }
@@ -195,6 +194,7 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
   h->max_smem = prop.sharedMemPerBlockOptin;
   const Geometry& g = h->g;
   if (g.pf < 256) { delete h; return fail(ROAR_ERR_UNSUPPORTED, "pyin_frame_length < 256 is not supported"); }
+  if (g.ph % 4 != 0) { delete h; return fail(ROAR_ERR_UNSUPPORTED, "pyin hop length must be a multiple of 4"); }
   if (g.npb > 1024 || g.npb < 2 * g.hw + 2) { delete h; return fail(ROAR_ERR_UNSUPPORTED, "pitch-bin count out of range"); }
   if (g.min_period < 1 || g.n_lags < 3 || g.max_period >= g.pf - g.pw) { delete h; return fail(ROAR_ERR_INVALID_ARG, "pyin period range empty"); }
   const char* env_tma = getenv("ROAR_SUP_NO_TMA");
@@ -224,22 +224,41 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
   // ---- K2 / K3 tables
   {
     PyinTables t = make_pyin_tables(*cfg, g);
-    std::vector<cf64> tw = make_twiddles<cf64, double>(g.pf, g.pf);
-    std::vector<cf64> twf = make_pass_twiddles<cf64, double>(g.pf), twh = make_pass_twiddles<cf64, double>(g.pf / 2);
-    UP(tw, d_tw64) UP(twf, d_tw64_f) UP(twh, d_tw64_h) UP(t.thresholds, d_thr) UP(t.beta_probs, d_beta) UP(t.beta_cum, d_beta_cum)
+    UP(t.thresholds, d_thr) UP(t.beta_probs, d_beta) UP(t.beta_cum, d_beta_cum)
     UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(t.lt_rows, d_lt_rows) UP(t.row_id, d_row_id)
     UP(t.freqs, d_freqs)
     h->n_rows = t.n_rows; h->lt0 = t.lt0; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
-    h->pyin_P = g.pf / 8;
-    h->pyin_G = 256 / h->pyin_P < 1 ? 1 : 256 / h->pyin_P;
-    h->pyin_FT = g.pf <= 1024 ? 16 : 8;
-    if (h->pyin_FT < h->pyin_G) h->pyin_FT = h->pyin_G;
-    h->pyin_span = (h->pyin_FT - 1) * g.ph + g.pf;
+    // K2a tiling: frames per tile chosen for (i) two CTAs per SM, (ii) little block overhead
+    // (a tile of ft frames computes ft + nb - 1 blocks), (iii) a chunk count that fills the 8 warps
+    cmnd_blocking(g.pw, g.ph, &h->pyin_BL, &h->pyin_nb);
+    h->pyin_ngroups = (g.max_period + 1 + ACF_R - 1) / ACF_R;
+    {
+      const size_t budget = (h->max_smem + 1024) / 2 - 1024;   // per-SM shared memory / 2, minus the per-CTA reserve
+      int best = 0; double best_score = -1.0;
+      for (int pass = 0; pass < 2 && best == 0; ++pass) {
+        for (int ft = 1; ft <= 32; ++ft) {
+          h->pyin_FT = ft;
+          h->pyin_ylen = cmnd_ylen(ft, g.pf, g.ph, h->pyin_BL, h->pyin_nb, h->pyin_ngroups);
+          PyinParams pp = pyin_params_base(h);
+          const size_t need = cmnd_smem_carve(pp, nullptr, nullptr);
+          if (need > (pass == 0 ? budget : h->max_smem)) break;
+          const int chunks = (ft + h->pyin_nb - 1) * cmnd_cpb(pp);
+          const double score = (double)ft / (ft + h->pyin_nb - 1) * chunks / (8.0 * ((chunks + 7) / 8));
+          if (score > best_score) { best_score = score; best = ft; }
+        }
+      }
+      if (best == 0) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "pYIN tile does not fit in shared memory"); }
+      h->pyin_FT = best;
+      h->pyin_ylen = cmnd_ylen(best, g.pf, g.ph, h->pyin_BL, h->pyin_nb, h->pyin_ngroups);
+    }
     PyinParams pp = pyin_params_base(h);
     h->cmnd_smem = cmnd_smem_carve(pp, nullptr, nullptr);
     h->prob_smem = prob_smem_carve(pp, nullptr, nullptr) * 8 + sizeof(double) * (g.n_thr + 2);
     if (h->cmnd_smem > h->max_smem || h->prob_smem > h->max_smem) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "pYIN tile does not fit in shared memory"); }
     CUDA_TRY(cudaFuncSetAttribute(k_pyin_cmnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cmnd_smem));
+    h->energy_smem = sizeof(float) * (size_t)(epad(energy_span(pp), g.ph) + 4);
+    if (h->energy_smem > h->max_smem) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "pYIN energy tile does not fit in shared memory"); }
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->energy_smem));
     CUDA_TRY(cudaFuncSetAttribute(k_pyin_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->prob_smem));
     h->vit_threads = (g.npb + 31) / 32 * 32;
     if (h->vit_threads < g.kmax) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "kmax exceeds Viterbi block size"); }
@@ -315,8 +334,9 @@ int roar_sup_pyin_geometry(const roar_sup_handle* h, int32_t out8[8]) {
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct PyinWs {
-  int32_t *tile_off, *order, *hist, *last_state, *n_cand;
+  int32_t *tile_off, *etile_off, *order, *hist, *last_state, *n_cand;
   double *big, *cand_lp, *lp_unv;
+  float* energy;
   uint16_t* cand_bin;
   size_t total;
 };
@@ -327,12 +347,14 @@ static PyinWs pyin_ws_layout(const roar_sup_handle* h, int32_t n_utts, int64_t f
   auto take = [&](size_t bytes) { unsigned char* p = base ? base + o : nullptr; o += a256(bytes); return p; };
   w.tile_off = (int32_t*)take(sizeof(int32_t) * (n_utts + 1));
   w.order = (int32_t*)take(sizeof(int32_t) * (n_utts + 1));
+  w.etile_off = (int32_t*)take(sizeof(int32_t) * (n_utts + 1));
   w.hist = (int32_t*)take(sizeof(int32_t) * ((size_t)max_T + 2));
   w.last_state = (int32_t*)take(sizeof(int32_t) * (n_utts + 1));
   w.n_cand = (int32_t*)take(sizeof(int32_t) * (frames + 1));
   w.lp_unv = (double*)take(sizeof(double) * (frames + 1));
   w.cand_lp = (double*)take(sizeof(double) * (size_t)frames * g.kmax);
   w.cand_bin = (uint16_t*)take(sizeof(uint16_t) * (size_t)frames * g.kmax);
+  w.energy = (float*)take(sizeof(float) * (size_t)frames * (g.max_period + 1));
   size_t a = sizeof(double) * (size_t)frames * g.n_lags, b = sizeof(uint16_t) * (size_t)frames * 2 * g.npb;
   w.big = (double*)take(a > b ? a : b);
   w.total = o;
@@ -383,11 +405,13 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
 
   PyinParams p = pyin_params_base(h);
   p.audio = d_audio; p.sample_off = d_sample_off; p.sample_len = d_sample_len; p.frame_off = d_frame_off;
-  p.tile_off = w.tile_off; p.n_utts = n_utts; p.cmnd = w.big; p.cand_bin = w.cand_bin; p.cand_lp = w.cand_lp;
+  p.tile_off = w.tile_off; p.n_utts = n_utts; p.cmnd = w.big; p.energy = w.energy; p.etile_off = w.etile_off; p.cand_bin = w.cand_bin; p.cand_lp = w.cand_lp;
   p.n_cand = w.n_cand; p.lp_unvoiced = w.lp_unv; p.voiced_prob = d_vprob; p.total_frames = total_frames;
   LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, p.FT, w.tile_off));
   const int64_t max_tiles = total_frames / p.FT + n_utts;
-  LAUNCH(h, ROAR_K_PYIN_CMND, st, k_pyin_cmnd<<<(unsigned)max_tiles, 256, h->cmnd_smem, st>>>(p));
+  LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, ENERGY_FT, w.etile_off));
+  LAUNCH(h, ROAR_K_PYIN_ENERGY, st, k_pyin_energy<<<(unsigned)(total_frames / ENERGY_FT + n_utts), 32, h->energy_smem, st>>>(p));
+  LAUNCH(h, ROAR_K_PYIN_CMND, st, k_pyin_cmnd<<<(unsigned)max_tiles, CMND_THREADS, h->cmnd_smem, st>>>(p));
   int64_t pb = (total_frames + 7) / 8;
   const int64_t cap = (int64_t)h->sm_count * 16;
   if (pb > cap) pb = cap;

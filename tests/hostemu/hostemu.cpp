@@ -88,19 +88,18 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
   if (!validate(*cfg).empty()) return -1;
   Geometry g = geometry(*cfg);
   PyinTables tb = make_pyin_tables(*cfg, g);
-  std::vector<cf64> tw = make_twiddles<cf64, double>(g.pf, g.pf);
-  std::vector<cf64> twf = make_pass_twiddles<cf64, double>(g.pf), twh = make_pass_twiddles<cf64, double>(g.pf / 2);
   const int NT = 256;
   PyinParams p;
   memset(&p, 0, sizeof(p));
-  p.F = g.pf; p.W = g.pw; p.hop = g.ph; p.H = g.pf / 2;
+  p.F = g.pf; p.W = g.pw; p.hop = g.ph;
   p.min_period = g.min_period; p.max_period = g.max_period; p.n_lags = g.n_lags;
-  p.P = g.pf / 8; p.G = NT / p.P < 1 ? 1 : NT / p.P;
-  p.FT = g.pf <= 1024 ? 16 : 8; if (p.FT < p.G) p.FT = p.G;
-  p.span = (p.FT - 1) * g.ph + g.pf;
+  p.FT = g.pf <= 1024 ? 15 : 6;
+  cmnd_blocking(g.pw, g.ph, &p.BL, &p.nb);
+  p.n_groups = (g.max_period + 1 + ACF_R - 1) / ACF_R;
+  p.ylen = cmnd_ylen(p.FT, g.pf, g.ph, p.BL, p.nb, p.n_groups);
   p.npb = g.npb; p.nbps = g.nbps; p.kmax = g.kmax; p.n_thr = g.n_thr;
   p.sr = cfg->sample_rate; p.fmin = cfg->pitch_fmin; p.no_trough_prob = cfg->no_trough_prob;
-  p.tw = tw.data(); p.tw_f = twf.data(); p.tw_h = twh.data(); p.thresholds = tb.thresholds.data(); p.beta_probs = tb.beta_probs.data();
+  p.thresholds = tb.thresholds.data(); p.beta_probs = tb.beta_probs.data();
   p.beta_cum = tb.beta_cum.data(); p.boltz_exp = tb.boltz_exp.data(); p.boltz_fact = tb.boltz_fact.data();
   const int64_t T = 1 + L / g.ph;
   int64_t sample_off[1] = {0}; int32_t sample_len[1] = {(int32_t)L};
@@ -114,61 +113,33 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
   p.tile_off = tile_off; p.n_utts = 1; p.cmnd = cmnd.data(); p.cand_bin = cand_bin.data();
   p.cand_lp = cand_lp.data(); p.n_cand = n_cand.data(); p.lp_unvoiced = lp_unv.data(); p.voiced_prob = vprob;
   p.total_frames = T;
-  // ---- K2a
+  // ---- K2a-0 energy, K2a
+  std::vector<float> en((size_t)T * (g.max_period + 1));
+  p.energy = en.data();
+  {
+    std::vector<float> ys((size_t)epad(energy_span(p), g.ph) + 4);
+    for (int64_t t0 = 0; t0 < T; t0 += ENERGY_FT) {
+      const int nf = (int)(T - t0 < ENERGY_FT ? T - t0 : ENERGY_FT);
+      const int n = (nf - 1) * g.ph + g.pw + g.max_period + 1;
+      for (int l = 0; l < 32; ++l) pyin_energy_stage(p, audio, (int)L, t0 * g.ph - g.pf / 2, n, ys.data(), l, 32);
+      for (int l = 0; l < nf; ++l) pyin_energy_frame(p, ys.data(), l, en.data() + t0 + l, (size_t)T);
+    }
+  }
   std::vector<unsigned char> smem(cmnd_smem_carve(p, nullptr, nullptr) + 64);
-  std::vector<cf64> regs((size_t)NT * 8);
-  const FftPlan planF = make_plan(p.F), planH = make_plan(p.H);
-  const size_t FP = (size_t)pidx(p.F);
   for (int tile = 0; tile < n_tiles; ++tile) {
     CmndSmem s;
     cmnd_smem_carve(p, smem.data(), &s);
     PyinTile t;
     if (!pyin_locate(p, tile, &t)) continue;
     for (int tid = 0; tid < NT; ++tid) cmnd_phase_load(p, t, s, tid, NT);
-    for (int tid = 0; tid < NT; ++tid) cmnd_phase_energy(p, t, s, tid, NT);
-    const int n_groups = (t.nf + p.G - 1) / p.G;
-    for (int gi = 0; gi < n_groups; ++gi) {
-      for (int tid = 0; tid < NT; ++tid) cmnd_first_pass(p, t, s, gi, tid);
-      int Ns = 8;
-      for (int ps = 1; ps < planF.n_pass; ++ps) {
-        const int R = planF.radix[ps];
-        for (int tid = 0; tid < NT; ++tid) {
-          cf64* r = regs.data() + (size_t)tid * 8;
-          if (R == 8) cmnd_pass_compute<8, false>(p, t, s, gi, tid, p.F, Ns, p.tw_f + planF.tw_off[ps], s.buf, FP, r);
-          else if (R == 4) cmnd_pass_compute<4, false>(p, t, s, gi, tid, p.F, Ns, p.tw_f + planF.tw_off[ps], s.buf, FP, r);
-          else cmnd_pass_compute<2, false>(p, t, s, gi, tid, p.F, Ns, p.tw_f + planF.tw_off[ps], s.buf, FP, r);
-        }
-        for (int tid = 0; tid < NT; ++tid) {
-          const cf64* r = regs.data() + (size_t)tid * 8;
-          if (R == 8) cmnd_pass_store<8>(p, t, gi, tid, p.F, Ns, s.buf, FP, r);
-          else if (R == 4) cmnd_pass_store<4>(p, t, gi, tid, p.F, Ns, s.buf, FP, r);
-          else cmnd_pass_store<2>(p, t, gi, tid, p.F, Ns, s.buf, FP, r);
-        }
-        Ns *= R;
-      }
-      for (int tid = 0; tid < NT; ++tid) cmnd_phase_product(p, t, s, gi, tid);
-      for (int tid = 0; tid < NT; ++tid) cmnd_phase_pack_inverse(p, t, s, gi, tid);
-      Ns = 1;
-      for (int ps = 0; ps < planH.n_pass; ++ps) {
-        const int R = planH.radix[ps];
-        for (int tid = 0; tid < NT; ++tid) {
-          cf64* r = regs.data() + (size_t)tid * 8;
-          if (R == 8) cmnd_pass_compute<8, true>(p, t, s, gi, tid, p.H, Ns, p.tw_h + planH.tw_off[ps], s.buf, FP, r);
-          else if (R == 4) cmnd_pass_compute<4, true>(p, t, s, gi, tid, p.H, Ns, p.tw_h + planH.tw_off[ps], s.buf, FP, r);
-          else cmnd_pass_compute<2, true>(p, t, s, gi, tid, p.H, Ns, p.tw_h + planH.tw_off[ps], s.buf, FP, r);
-        }
-        for (int tid = 0; tid < NT; ++tid) {
-          const cf64* r = regs.data() + (size_t)tid * 8;
-          if (R == 8) cmnd_pass_store<8>(p, t, gi, tid, p.H, Ns, s.buf, FP, r);
-          else if (R == 4) cmnd_pass_store<4>(p, t, gi, tid, p.H, Ns, s.buf, FP, r);
-          else cmnd_pass_store<2>(p, t, gi, tid, p.H, Ns, s.buf, FP, r);
-        }
-        Ns *= R;
-      }
-      for (int tid = 0; tid < NT; ++tid) cmnd_phase_diff(p, t, s, gi, tid, s.buf);
-      for (int tid = 0; tid < NT; ++tid) cmnd_phase_scan1(p, t, s, gi, tid);
-      for (int tid = 0; tid < NT; ++tid) cmnd_phase_scan2(p, t, s, gi, tid, s.chunk + (size_t)p.G * 32);
-      for (int tid = 0; tid < NT; ++tid) cmnd_phase_emit(p, t, s, gi, tid, s.chunk + (size_t)p.G * 32);
+    const int n_units = cmnd_n_blocks(p, t.nf) * p.n_groups;
+    for (int u = 0; u < n_units; ++u) cmnd_acf_unit(p, s, u / p.n_groups, u % p.n_groups);
+    for (int tid = 0; tid < NT; ++tid) cmnd_phase_diff(p, t, s, tid, NT);
+    for (int f = 0; f < t.nf; ++f) {
+      const int slot = f % CMND_SLOTS;
+      for (int l = 0; l < 32; ++l) cmnd_phase_scan1(p, s, f, slot, l);
+      for (int l = 0; l < 32; ++l) cmnd_phase_scan2(p, s, slot, l);
+      for (int l = 0; l < 32; ++l) cmnd_phase_emit(p, t, s, f, slot, l);
     }
   }
   if (cmnd_out) memcpy(cmnd_out, cmnd.data(), cmnd.size() * sizeof(double));
