@@ -39,6 +39,9 @@ struct VitParams {
   float* f0;                    // [frames]
   float* voiced_flag;           // [frames]
   int32_t lt_in_smem;
+  double lt_max;                // largest banded table entry
+  const double* gap1;           // [n_warps] narrow-band gaps (fast path), see vit3_pick_half
+  const double* gap5;
 };
 
 struct VitBest { double v; int k; };
@@ -181,6 +184,383 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
     double vmax = lane < nwarp ? wv[rb + lane] : -1e308;
     int kstar = lane < nwarp ? wk[rb + lane] : 0x7fffffff;
     vit_warp_argmax(vmax, kstar);
+    if (lane == 0) p.last_state[utt] = kstar;
+  }
+}
+
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------------------
+// K3 fast path (transition width 51, the reference's geometry at hop = frame/4 and sr >= 22.05 kHz).
+//
+// Same recursion, same float64 adds, same first-index arg-max -- but sources that provably cannot win
+// are not visited:
+//   * DEAD sources.  Every destination j receives an offer >= fl(vmax + lt0) from the global arg-max
+//     k* (in band: fl(vmax + lt[k*,j]) with lt >= lt0; out of band: fl(vmax + lt0)).  A source s with
+//     V[s] < fl(vmax + lt0) offers fl(V[s] + lt) <= V[s] (lt < 0), strictly less: it never wins, never
+//     ties.  While step t computes V[t,.], each thread compares its two new values with
+//     thr' = fl(LB + lt0), LB <= vmax_t being the value of the best one-step continuation of k*_{t-1}
+//     (known before the step), and appends the survivors to a per-voicing LIVE LIST.  thr' <= the true
+//     threshold, so the list is a superset of the live states.  Step t+1 walks the list when it holds
+//     <= VIT_LIST_MAX entries (voiced stretches: a handful of candidates), otherwise scans the band.
+//   * DOMINATED voiced sources.  When the voiced list overflowed, voiced offers are bounded by
+//     Wc = fl(vvmax + lt_max) (vvmax = exact max over voiced V[t-1,.], lt_max = largest table entry).
+//     If the best offer so far (unvoiced band scan + out-of-band) is > Wc for both destination
+//     voicings, the voiced band scan is skipped (unvoiced stretches); otherwise it runs.
+// Both rules only skip sources that lose strictly, so values, back-pointers and the decoded path are
+// bit-identical to the dense recursion (checked against it in tests/).
+//
+// The band scan is fully unrolled (51 sources): V rows are padded by hw sentinels (-1e308) on both
+// sides and a zero row is appended to the table for them, row ids of a thread's 51 sources are packed
+// 5 x 6 bit per register once per utterance, so one scan step is LDS.64 + bit-field + LDS.128 + 2 DADD
+// + 2 compare/select.
+constexpr int VIT_TW = 51;
+constexpr int VIT_HW = 25;
+constexpr int VIT_LIST_MAX = 64;
+constexpr int VIT_RID_REGS = (VIT_TW + 4) / 5;   // 11
+constexpr double VIT_NEG = -1e308;
+
+struct alignas(16) VitLive { double v; int32_t kb; int32_t row; };
+
+struct VitBest2 { double b; int a; };
+HD void vit_offer(VitBest2& x, double s, int idx) {
+  if (s > x.b || (s == x.b && idx < x.a)) { x.b = s; x.a = idx; }
+}
+
+// packed row ids of sources j-hw .. j+hw (row `zero_row` for sources outside [0, npb))
+HD void vit_pack_rows(const uint16_t* row_id, int npb, int zero_row, int j, uint32_t* rid) {
+  for (int r = 0; r < VIT_RID_REGS; ++r) rid[r] = 0;
+  for (int d = 0; d < VIT_TW; ++d) {
+    const int i = j - VIT_HW + d;
+    const uint32_t row = (i >= 0 && i < npb) ? row_id[i] : (uint32_t)zero_row;
+    rid[d / 5] |= row << (6 * (d % 5));
+  }
+}
+
+// band scan over one source voicing.  Vp = &Vsrc_padded[j] (source i = j-hw+d sits at Vp[d]).
+// same/swit: best offers for the destination of the same / the other voicing; d_* = winning d.
+HD void vit_band_scan(const double* Vp, const cf64* lt2, const uint32_t* rid, double* same_b, int* same_d,
+                      double* swit_b, int* swit_d) {
+  // three independent running maxima (sources 0-16, 17-33, 34-50) merged in source order with a strict
+  // compare: same first-index arg-max as one chain, three times the instruction-level parallelism
+  double b0[3], b1[3];
+  int d0[3], d1[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { b0[c] = VIT_NEG; b1[c] = VIT_NEG; d0[c] = 0; d1[c] = 0; }
+#pragma unroll
+  for (int q = 0; q < 17; ++q) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int d = c * 17 + q;
+      const double v = Vp[d];
+      const uint32_t row = (rid[d / 5] >> (6 * (d % 5))) & 63u;
+      const cf64 e = lt2[row * VIT_TW + (2 * VIT_HW - d)];
+      const double s0 = v + e.x, s1 = v + e.y;
+      if (s0 > b0[c]) { b0[c] = s0; d0[c] = d; }
+      if (s1 > b1[c]) { b1[c] = s1; d1[c] = d; }
+    }
+  }
+#pragma unroll
+  for (int c = 1; c < 3; ++c) {
+    if (b0[c] > b0[0]) { b0[0] = b0[c]; d0[0] = d0[c]; }
+    if (b1[c] > b1[0]) { b1[0] = b1[c]; d1[0] = d1[c]; }
+  }
+  *same_b = b0[0]; *same_d = d0[0]; *swit_b = b1[0]; *swit_d = d1[0];
+}
+// the same over sources j-D .. j+D only (see the narrow-band rule in vit3_step_bin)
+template <int D>
+HD void vit_band_scan_narrow(const double* Vp, const cf64* lt2, const uint32_t* rid, double* same_b, int* same_d,
+                             double* swit_b, int* swit_d) {
+  double b0 = VIT_NEG, b1 = VIT_NEG;
+  int d0 = 0, d1 = 0;
+#pragma unroll
+  for (int d = VIT_HW - D; d <= VIT_HW + D; ++d) {
+    const double v = Vp[d];
+    const uint32_t row = (rid[d / 5] >> (6 * (d % 5))) & 63u;
+    const cf64 e = lt2[row * VIT_TW + (2 * VIT_HW - d)];
+    const double s0 = v + e.x, s1 = v + e.y;
+    if (s0 > b0) { b0 = s0; d0 = d; }
+    if (s1 > b1) { b1 = s1; d1 = d; }
+  }
+  *same_b = b0; *same_d = d0; *swit_b = b1; *swit_d = d1;
+}
+
+// one live-list entry against destination bin j: `same` gets e.v + ls, `swit` gets e.v + lc
+HD void vit_list_offer(const VitLive& e, int state_base, const cf64* lt2, int j, VitBest2& same, VitBest2& swit) {
+  const int dd = j - e.kb + VIT_HW;
+  if ((unsigned)dd <= 2u * VIT_HW) {
+    const cf64 l = lt2[e.row * VIT_TW + dd];
+    vit_offer(same, e.v + l.x, state_base + e.kb);
+    vit_offer(swit, e.v + l.y, state_base + e.kb);
+  }
+}
+
+struct Vit3Step {
+  // sources (time t-1)
+  const double* Vv;       // padded rows: element i at [i + hw]
+  const double* Vu;
+  const VitLive* Lv; int nv;   // nv > VIT_LIST_MAX: overflow
+  const VitLive* Lu; int nu;
+  double vmax; int kstar;      // first global arg-max of V[t-1]
+  double vvmax;                // max over the voiced V[t-1] a destination of this warp can see in band
+  int u_half;                  // unvoiced band scan half-width for this warp: 25 (full), 5 or 1
+  // tables
+  const cf64* lt2;             // [n_rows+1][51] (ls, lc), last row zeros
+  double lt0, lt_max;
+  int npb;
+};
+
+// NARROW-BAND rule for the unvoiced scan of warp w (32 consecutive destination bins).  Let
+// delta = max(Vu over the bins of warps w-1, w, w+1) - min(Vu over the bins of warp w) and
+// G_D[w] = min over destinations j of w, in-band sources k with |k-j| > D and both table components of
+// (lt[j->j] - lt[k->j]) (host table, exact).  If delta < G_D[w] - 1e-6, every source farther than D
+// offers strictly less than the destination's own bin does (rounding moves either side by < 1e-10),
+// so scanning j-D .. j+D yields the same arg-max.  Flat stretches of Vu (most of an unvoiced passage,
+// and everything away from the candidates in a voiced one) need D = 1.
+HD int vit3_pick_half(double delta, double g1, double g5) {
+#ifndef VIT_NARROW_BAND
+  (void)delta; (void)g1; (void)g5; return VIT_HW;   // see DESIGN.md: per-warp narrowing lengthens the per-step critical path
+#endif
+  if (delta < g1 - 1e-6) return 1;
+  (void)g5;   // a half-width-5 tier was measured: it fires on < 1 % of the scans, not worth the code
+  return VIT_HW;
+}
+
+// new values and back-pointers of pitch bin j
+HD void vit3_step_bin(const Vit3Step& c, int j, const uint32_t* rid, double lp_v, double lp_u, double* out_v,
+                      double* out_u, int* ptr_v, int* ptr_u) {
+  VitBest2 bv, bu;                       // destination voiced / unvoiced
+  bv.b = VIT_NEG; bv.a = 0x7fffffff; bu = bv;
+  {
+    const int ks = c.kstar >= c.npb ? c.kstar - c.npb : c.kstar;
+    const int dist = ks > j ? ks - j : j - ks;
+    if (dist > VIT_HW) { const double so = c.vmax + c.lt0; vit_offer(bv, so, c.kstar); vit_offer(bu, so, c.kstar); }
+  }
+  if (c.nu > VIT_LIST_MAX) {
+    double sb, wb; int sd, wd;
+    if (c.u_half == 1) vit_band_scan_narrow<1>(c.Vu + j, c.lt2, rid, &sb, &sd, &wb, &wd);
+    else vit_band_scan(c.Vu + j, c.lt2, rid, &sb, &sd, &wb, &wd);
+    vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
+    vit_offer(bv, wb, c.npb + j - VIT_HW + wd);
+  } else {
+    for (int e = 0; e < c.nu; ++e) vit_list_offer(c.Lu[e], c.npb, c.lt2, j, bu, bv);
+  }
+  if (c.nv > VIT_LIST_MAX) {
+    const double Wc = c.vvmax + c.lt_max;
+    if (!(bv.b > Wc && bu.b > Wc)) {
+      double sb, wb; int sd, wd;
+      vit_band_scan(c.Vv + j, c.lt2, rid, &sb, &sd, &wb, &wd);
+      vit_offer(bv, sb, j - VIT_HW + sd);
+      vit_offer(bu, wb, j - VIT_HW + wd);
+    }
+  } else {
+    for (int e = 0; e < c.nv; ++e) vit_list_offer(c.Lv[e], 0, c.lt2, j, bv, bu);
+  }
+  *out_v = lp_v + bv.b; *out_u = lp_u + bu.b;
+  *ptr_v = bv.a; *ptr_u = bu.a;
+}
+
+// lower bound on vmax_t: the best one-step continuation of k*_{t-1} into the unvoiced state of its own
+// bin or into one of frame t's candidate bins.  `lane`/`nl` stride the candidate list (nl = 1 on the host).
+HD double vit3_lower_bound(const Vit3Step& c, const uint16_t* row_id, double lp_u, const uint16_t* cbin,
+                           const double* clp, int nc, int lane, int nl) {
+  const int ks = c.kstar >= c.npb ? c.kstar - c.npb : c.kstar;
+  const bool kv = c.kstar < c.npb;
+  const cf64* row = c.lt2 + (int)row_id[ks] * VIT_TW;
+  double lb = VIT_NEG;
+  if (lane == 0) { const cf64 e = row[VIT_HW]; lb = lp_u + (c.vmax + (kv ? e.y : e.x)); }
+  for (int q = lane; q < nc; q += nl) {
+    const int b = cbin[q];
+    const int dd = b - ks + VIT_HW;
+    double l = c.lt0;
+    if ((unsigned)dd <= 2u * VIT_HW) { const cf64 e = row[dd]; l = kv ? e.x : e.y; }
+    const double cand = clp[q] + (c.vmax + l);
+    if (cand > lb) lb = cand;
+  }
+  return lb;
+}
+
+#ifdef __CUDACC__
+// Warp reductions over NEGATIVE finite doubles with redux.sync: for negative values, larger value <=>
+// smaller (hi, lo) bit pattern as unsigned.  Every V of this HMM is < 0 (sums of logs of
+// probabilities), and the fillers are -1e308 (max) / -0.0 (min).
+__device__ __forceinline__ double vit_warp_max(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  return __hiloint2double((int)mhi, (int)mlo);
+}
+__device__ __forceinline__ double vit_warp_min(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  return __hiloint2double((int)mhi, (int)mlo);
+}
+// (max value, smallest index attaining it)
+__device__ __forceinline__ void vit_warp_argmax_neg(double& v, int& k) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  const bool is = hi == mhi && lo == mlo;
+  k = (int)__reduce_min_sync(0xffffffffu, is ? (unsigned)k : 0x7fffffffu);
+  v = __hiloint2double((int)mhi, (int)mlo);
+}
+
+// fixed shared-memory layout (compile-time offsets: nothing to re-derive per step)
+constexpr int VIT_NPB_MAX = 608;
+constexpr int VIT_VP_MAX = VIT_NPB_MAX + 2 * VIT_HW;
+constexpr int VIT_KMAX_MAX = 352;
+constexpr int VIT_ROWS_MAX = 64;
+struct alignas(16) Vit3Shared {
+  cf64 lt2[VIT_ROWS_MAX * VIT_TW];           // banded rows + one zero row
+  double Vv[2][VIT_VP_MAX];                  // padded value rows, double-buffered on step parity
+  double Vu[2][VIT_VP_MAX];
+  double lpv[2][VIT_NPB_MAX];                // sparse voiced observations of the frame being entered
+  double clp[2][VIT_KMAX_MAX];               // its candidate list (log-prob, bin)
+  VitLive Lv[3][VIT_LIST_MAX];               // live lists: slot t % 3
+  VitLive Lu[3][VIT_LIST_MAX];
+  double wv[2][32], wvv[2][32], wumax[2][32], wumin[2][32];   // per-warp partials (= 32-bin segment stats)
+  double g1[32], g5[32];                     // narrow-band gaps per warp
+  int wk[2][32];
+  int cnt[3][2];
+  int pad_[2];
+  uint16_t cbin[2][VIT_KMAX_MAX];
+  uint16_t rowid[VIT_NPB_MAX];
+};
+
+// warp-aggregated append of the live states of one voicing
+__device__ __forceinline__ void vit3_append(bool live, double v, int kb, int row, VitLive* L, int* cnt, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, live);
+  if (m == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(cnt, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (live) {
+    const int pos = base + __popc(m & ((1u << lane) - 1u));
+    if (pos < VIT_LIST_MAX) { VitLive e; e.v = v; e.kb = kb; e.row = row; L[pos] = e; }
+  }
+}
+
+// blockDim.x = npb rounded up to a warp multiple (<= 608); two CTAs (utterances) per SM
+__global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Vit3Shared& s = *reinterpret_cast<Vit3Shared*>(smem_raw);
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int utt = p.order[blockIdx.x];
+  const int64_t f0 = p.frame_off[utt];
+  const int T = (int)(p.frame_off[utt + 1] - f0);
+  if (T <= 0) return;
+  const int npb = p.npb, kmax = p.kmax, zero_row = p.n_rows;
+  {
+    const int n = p.n_rows * VIT_TW;
+    const cf64* src = reinterpret_cast<const cf64*>(p.lt_rows);
+    for (int i = tid; i < n; i += nthr) s.lt2[i] = src[i];
+    for (int i = tid; i < VIT_TW; i += nthr) { cf64 z; z.x = 0.0; z.y = 0.0; s.lt2[n + i] = z; }
+    for (int i = tid; i < npb; i += nthr) { s.rowid[i] = p.row_id[i]; s.lpv[0][i] = p.lt0; s.lpv[1][i] = p.lt0; }
+    for (int i = tid; i < VIT_VP_MAX; i += nthr) { s.Vv[0][i] = VIT_NEG; s.Vv[1][i] = VIT_NEG; s.Vu[0][i] = VIT_NEG; s.Vu[1][i] = VIT_NEG; }
+    if (tid < 32) { s.g1[tid] = tid < nwarp ? p.gap1[tid] : 0.0; s.g5[tid] = tid < nwarp ? p.gap5[tid] : 0.0; }
+    if (tid < 6) (&s.cnt[0][0])[tid] = tid < 2 ? VIT_LIST_MAX + 1 : 0;   // time 0: scan everything
+  }
+  const int j = tid;
+  uint32_t rid[VIT_RID_REGS];
+  vit_pack_rows(p.row_id, npb, zero_row, j < npb ? j : 0, rid);
+  __syncthreads();
+  // frame 0 observations
+  int nc_cur = p.n_cand[f0];
+  if (tid < nc_cur) s.lpv[0][p.cand_bin[(size_t)f0 * kmax + tid]] = p.cand_lp[(size_t)f0 * kmax + tid];
+  __syncthreads();
+  double bestv = VIT_NEG, vvb = VIT_NEG, umx = VIT_NEG, umn = -0.0; int bestk = 0x7fffffff;
+  if (j < npb) {
+    const double vv = s.lpv[0][j] + p.li_voiced;
+    const double vu = p.lp_unvoiced[f0] + p.li_unvoiced;
+    s.lpv[0][j] = p.lt0;
+    s.Vv[0][VIT_HW + j] = vv; s.Vu[0][VIT_HW + j] = vu;
+    bestv = vv; bestk = j; vvb = vv; umx = vu; umn = vu;
+    if (vu > bestv) { bestv = vu; bestk = npb + j; }
+  }
+  double lp_u_next = 0.0;
+  if (T > 1) {
+    nc_cur = p.n_cand[f0 + 1];
+    lp_u_next = p.lp_unvoiced[f0 + 1];
+    if (tid < nc_cur) {
+      const uint16_t b = p.cand_bin[(size_t)(f0 + 1) * kmax + tid];
+      const double l = p.cand_lp[(size_t)(f0 + 1) * kmax + tid];
+      s.lpv[1][b] = l; s.cbin[1][tid] = b; s.clp[1][tid] = l;
+    }
+  }
+  vit_warp_argmax_neg(bestv, bestk);
+  vvb = vit_warp_max(vvb); umx = vit_warp_max(umx); umn = vit_warp_min(umn);
+  if (lane == 0) { s.wv[0][warp] = bestv; s.wk[0][warp] = bestk; s.wvv[0][warp] = vvb; s.wumax[0][warp] = umx; s.wumin[0][warp] = umn; }
+  __syncthreads();
+
+  uint16_t* pr = p.ptr + (size_t)(f0 + 1) * (2 * npb);
+  for (int t = 1; t < T; ++t, pr += 2 * npb) {
+    const int rp = (t - 1) & 1, wp = t & 1;           // V / partial parity: read, write
+    const int rl = (t - 1) % 3, wl = t % 3, zl = (t + 1) % 3;   // live-list slots: read, write, reset
+    Vit3Step c;
+    {
+      double vmax = lane < nwarp ? s.wv[rp][lane] : VIT_NEG;
+      int kstar = lane < nwarp ? s.wk[rp][lane] : 0x7fffffff;
+      vit_warp_argmax_neg(vmax, kstar);
+      c.vmax = vmax; c.kstar = kstar;
+      // sources in band of this warp's destinations live in the 32-bin segments of warps w-1, w, w+1
+      double seg = s.wvv[rp][warp], um = s.wumax[rp][warp];
+      if (warp > 0) { const double x = s.wvv[rp][warp - 1], y = s.wumax[rp][warp - 1]; if (x > seg) seg = x; if (y > um) um = y; }
+      if (warp + 1 < nwarp) { const double x = s.wvv[rp][warp + 1], y = s.wumax[rp][warp + 1]; if (x > seg) seg = x; if (y > um) um = y; }
+      c.vvmax = seg;
+      c.u_half = vit3_pick_half(um - s.wumin[rp][warp], s.g1[warp], s.g5[warp]);
+    }
+    c.Vv = s.Vv[rp]; c.Vu = s.Vu[rp];
+    c.Lv = s.Lv[rl]; c.Lu = s.Lu[rl];
+    c.nv = s.cnt[rl][0]; c.nu = s.cnt[rl][1];
+    c.lt2 = s.lt2; c.lt0 = p.lt0; c.lt_max = p.lt_max; c.npb = npb;
+    if (tid < 2) s.cnt[zl][tid] = 0;
+    const double lp_u = lp_u_next;
+    // liveness threshold for the values this step produces
+    double thr;
+    {
+      double lb = vit3_lower_bound(c, s.rowid, lp_u, s.cbin[wp], s.clp[wp], nc_cur, lane, 32);
+      lb = vit_warp_max(lb);
+      thr = lb + p.lt0;
+    }
+    // prefetch next frame's sparse observations (consumed after the band work)
+    int nc_next = 0; unsigned nb_bin = 0; double nb_lp = 0.0;
+    if (t + 1 < T) {
+      nc_next = p.n_cand[f0 + t + 1];
+      lp_u_next = p.lp_unvoiced[f0 + t + 1];
+      if (tid < nc_next) {
+        nb_bin = p.cand_bin[(size_t)(f0 + t + 1) * kmax + tid];
+        nb_lp = p.cand_lp[(size_t)(f0 + t + 1) * kmax + tid];
+      }
+    }
+    bestv = VIT_NEG; bestk = 0x7fffffff; vvb = VIT_NEG; umx = VIT_NEG; umn = -0.0;
+    bool live_v = false, live_u = false;
+    double nv = VIT_NEG, nu = VIT_NEG;
+    if (j < npb) {
+      int av, au;
+      vit3_step_bin(c, j, rid, s.lpv[wp][j], lp_u, &nv, &nu, &av, &au);
+      s.lpv[wp][j] = p.lt0;
+      s.Vv[wp][VIT_HW + j] = nv; s.Vu[wp][VIT_HW + j] = nu;
+      pr[j] = (uint16_t)av; pr[npb + j] = (uint16_t)au;
+      bestv = nv; bestk = j; vvb = nv; umx = nu; umn = nu;
+      if (nu > bestv) { bestv = nu; bestk = npb + j; }
+      live_v = nv >= thr; live_u = nu >= thr;
+    }
+    const int myrow = j < npb ? (int)s.rowid[j] : 0;
+    vit3_append(live_v, nv, j, myrow, s.Lv[wl], &s.cnt[wl][0], lane);
+    vit3_append(live_u, nu, j, myrow, s.Lu[wl], &s.cnt[wl][1], lane);
+    if (tid < nc_next) { s.lpv[wp ^ 1][nb_bin] = nb_lp; s.cbin[wp ^ 1][tid] = (uint16_t)nb_bin; s.clp[wp ^ 1][tid] = nb_lp; }
+    nc_cur = nc_next;
+    vit_warp_argmax_neg(bestv, bestk);
+    vvb = vit_warp_max(vvb); umx = vit_warp_max(umx); umn = vit_warp_min(umn);
+    if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; s.wumax[wp][warp] = umx; s.wumin[wp][warp] = umn; }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    const int rb = (T - 1) & 1;
+    double vmax = lane < nwarp ? s.wv[rb][lane] : VIT_NEG;
+    int kstar = lane < nwarp ? s.wk[rb][lane] : 0x7fffffff;
+    vit_warp_argmax_neg(vmax, kstar);
     if (lane == 0) p.last_state[utt] = kstar;
   }
 }

@@ -46,8 +46,10 @@ struct roar_sup_handle {
   int pyin_FT = 15, pyin_BL = 0, pyin_nb = 0, pyin_ngroups = 0, pyin_ylen = 0; size_t cmnd_smem = 0, prob_smem = 0, energy_smem = 0;
   // K3
   double* d_lt_rows = nullptr; uint16_t* d_row_id = nullptr; double* d_freqs = nullptr;
-  int n_rows = 0; double lt0 = 0, li_v = 0, li_u = 0;
+  double *d_gap1 = nullptr, *d_gap5 = nullptr;
+  int n_rows = 0; double lt0 = 0, lt_max = 0, li_v = 0, li_u = 0;
   int vit_threads = 0; size_t vit_smem = 0; int lt_in_smem = 1;
+  int vit_fast = 0; size_t vit3_smem = 0;
   // K4
   double* d_lf = nullptr; int lf_n = 0;
   // optional per-kernel timing (diagnostics; not thread-safe)
@@ -226,8 +228,8 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     PyinTables t = make_pyin_tables(*cfg, g);
     UP(t.thresholds, d_thr) UP(t.beta_probs, d_beta) UP(t.beta_cum, d_beta_cum)
     UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(t.lt_rows, d_lt_rows) UP(t.row_id, d_row_id)
-    UP(t.freqs, d_freqs)
-    h->n_rows = t.n_rows; h->lt0 = t.lt0; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
+    UP(t.freqs, d_freqs) UP(t.gap1, d_gap1) UP(t.gap5, d_gap5)
+    h->n_rows = t.n_rows; h->lt0 = t.lt0; h->lt_max = t.lt_max; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
     // K2a tiling: frames per tile chosen for (i) two CTAs per SM, (ii) little block overhead
     // (a tile of ft frames computes ft + nb - 1 blocks), (iii) a chunk count that fills the 8 warps
     cmnd_blocking(g.pw, g.ph, &h->pyin_BL, &h->pyin_nb);
@@ -271,6 +273,14 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<false, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
     CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
     CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
+    // fast path: the reference geometry (transition width 51), row ids in 6 bits
+    h->vit3_smem = sizeof(Vit3Shared);
+    const char* env_gen = getenv("ROAR_SUP_VITERBI_GENERIC");
+    h->vit_fast = (g.tw == VIT_TW && t.n_rows + 1 <= VIT_ROWS_MAX && g.npb <= VIT_NPB_MAX && g.kmax <= VIT_KMAX_MAX &&
+                   h->vit3_smem <= h->max_smem &&
+                   !(env_gen && env_gen[0] == '1')) ? 1 : 0;
+    if (h->vit_fast)
+      CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi51, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit3_smem));
   }
   // ---- K4 log-factorial table
   {
@@ -431,8 +441,10 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
   v.lt_rows = h->d_lt_rows; v.row_id = h->d_row_id; v.lt0 = h->lt0; v.li_voiced = h->li_v; v.li_unvoiced = h->li_u;
   v.cand_bin = w.cand_bin; v.cand_lp = w.cand_lp; v.n_cand = w.n_cand; v.lp_unvoiced = w.lp_unv;
   v.ptr = (uint16_t*)w.big; v.last_state = w.last_state; v.freqs = h->d_freqs; v.f0 = d_f0; v.voiced_flag = d_vflag;
-  v.lt_in_smem = h->lt_in_smem;
-  if (h->vit_threads <= 640) {
+  v.lt_in_smem = h->lt_in_smem; v.lt_max = h->lt_max; v.gap1 = h->d_gap1; v.gap5 = h->d_gap5;
+  if (h->vit_fast) {
+    LAUNCH(h, ROAR_K_VITERBI, st, (k_pyin_viterbi51<<<n_utts, h->vit_threads, h->vit3_smem, st>>>(v)));
+  } else if (h->vit_threads <= 640) {
     if (h->lt_in_smem) LAUNCH(h, ROAR_K_VITERBI, st, (k_pyin_viterbi<true, 640><<<n_utts, h->vit_threads, h->vit_smem, st>>>(v)));
     else LAUNCH(h, ROAR_K_VITERBI, st, (k_pyin_viterbi<false, 640><<<n_utts, h->vit_threads, h->vit_smem, st>>>(v)));
   } else {

@@ -169,7 +169,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
       for (int l = 0; l < 32; ++l) prob_phase6b(p, s, fr, l);
     }
   }
-  // ---- K3 (same per-bin step function; the block argmax is a plain scan here)
+  // ---- K3 (same per-bin step functions; the block reductions are plain scans here)
   VitParams v;
   memset(&v, 0, sizeof(v));
   v.npb = g.npb; v.tw = g.tw; v.hw = g.hw; v.kmax = g.kmax; v.n_rows = tb.n_rows;
@@ -192,6 +192,67 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
   for (int c = 0; c < n_cand[0]; ++c) lpv[cand_bin[c]] = cand_lp[c];
   for (int j = 0; j < npb; ++j) { V[j].x = lpv[j] + tb.li_voiced; V[j].y = lp_unv[0] + tb.li_unvoiced; }
   for (int c = 0; c < n_cand[0]; ++c) lpv[cand_bin[c]] = tb.lt0;
+  const bool fast = g.tw == VIT_TW && tb.n_rows + 1 <= 64 && !getenv("ROAR_SUP_VITERBI_GENERIC");
+  if (fast) {
+    // fast path (k_pyin_viterbi51): padded V rows, live lists, dominance skipping
+    const int VP = npb + 2 * VIT_HW;
+    std::vector<double> Vv(2 * (size_t)VP, VIT_NEG), Vu(2 * (size_t)VP, VIT_NEG);
+    std::vector<cf64> lt2((size_t)(tb.n_rows + 1) * VIT_TW);
+    for (size_t i = 0; i < (size_t)tb.n_rows * VIT_TW; ++i) { lt2[i].x = tb.lt_rows[2 * i]; lt2[i].y = tb.lt_rows[2 * i + 1]; }
+    for (size_t i = (size_t)tb.n_rows * VIT_TW; i < lt2.size(); ++i) { lt2[i].x = 0; lt2[i].y = 0; }
+    std::vector<VitLive> Lv(3 * VIT_LIST_MAX), Lu(3 * VIT_LIST_MAX);
+    int cnt[3][2] = {{VIT_LIST_MAX + 1, VIT_LIST_MAX + 1}, {0, 0}, {0, 0}};
+    std::vector<uint32_t> rid((size_t)npb * VIT_RID_REGS);
+    for (int j = 0; j < npb; ++j) vit_pack_rows(tb.row_id.data(), npb, tb.n_rows, j, rid.data() + (size_t)j * VIT_RID_REGS);
+    for (int j = 0; j < npb; ++j) { Vv[VIT_HW + j] = V[j].x; Vu[VIT_HW + j] = V[j].y; }
+    long skipped = 0, listed = 0, half_hist[3] = {0, 0, 0};
+    for (int64_t t = 1; t < T; ++t) {
+      const int rp = (int)((t - 1) & 1), wp = (int)(t & 1), rl = (int)((t - 1) % 3), wl = (int)(t % 3), zl = (int)((t + 1) % 3);
+      Vit3Step c;
+      c.Vv = Vv.data() + (size_t)rp * VP; c.Vu = Vu.data() + (size_t)rp * VP;
+      c.vmax = -1e308; c.kstar = 0x7fffffff; c.vvmax = -1e308;
+      for (int b = 0; b < 2; ++b)
+        for (int j = 0; j < npb; ++j) {
+          const double val = b ? c.Vu[VIT_HW + j] : c.Vv[VIT_HW + j];
+          if (val > c.vmax) { c.vmax = val; c.kstar = b * npb + j; }
+          if (!b && val > c.vvmax) c.vvmax = val;
+        }
+      c.Lv = Lv.data() + (size_t)rl * VIT_LIST_MAX; c.Lu = Lu.data() + (size_t)rl * VIT_LIST_MAX;
+      c.nv = cnt[rl][0]; c.nu = cnt[rl][1];
+      c.lt2 = lt2.data(); c.lt0 = tb.lt0; c.lt_max = tb.lt_max; c.npb = npb;
+      cnt[zl][0] = cnt[zl][1] = 0;
+      if (c.nv <= VIT_LIST_MAX) ++listed; else ++skipped;
+      const double lb = vit3_lower_bound(c, tb.row_id.data(), lp_unv[t], cand_bin.data() + (size_t)t * g.kmax,
+                                         cand_lp.data() + (size_t)t * g.kmax, n_cand[t], 0, 1);
+      const double thr = lb + tb.lt0;
+      for (int q = 0; q < n_cand[t]; ++q) lpv[cand_bin[(size_t)t * g.kmax + q]] = cand_lp[(size_t)t * g.kmax + q];
+      for (int j = 0; j < npb; ++j) {
+        double nv, nu; int av, au;
+        {   // the kernel's per-warp statistics over the 32-bin segments w-1, w, w+1
+          const int w = j / 32, nw = (npb + 31) / 32;
+          double seg = -1e308, um = -1e308, umin = 0.0;
+          for (int ww = (w > 0 ? w - 1 : 0); ww <= (w + 1 < nw ? w + 1 : nw - 1); ++ww)
+            for (int q = ww * 32; q < ww * 32 + 32 && q < npb; ++q) {
+              if (c.Vv[VIT_HW + q] > seg) seg = c.Vv[VIT_HW + q];
+              if (c.Vu[VIT_HW + q] > um) um = c.Vu[VIT_HW + q];
+              if (ww == w && c.Vu[VIT_HW + q] < umin) umin = c.Vu[VIT_HW + q];
+            }
+          c.vvmax = seg;
+          c.u_half = vit3_pick_half(um - umin, tb.gap1[w], tb.gap5[w]);
+          if (c.nu > VIT_LIST_MAX && j % 32 == 0) ++half_hist[c.u_half == 1 ? 0 : c.u_half == 5 ? 1 : 2];
+        }
+        vit3_step_bin(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lpv[j], lp_unv[t], &nv, &nu, &av, &au);
+        Vv[(size_t)wp * VP + VIT_HW + j] = nv; Vu[(size_t)wp * VP + VIT_HW + j] = nu;
+        ptr[(size_t)t * 2 * npb + j] = (uint16_t)av; ptr[(size_t)t * 2 * npb + npb + j] = (uint16_t)au;
+        if (nv >= thr) { if (cnt[wl][0] < VIT_LIST_MAX) { VitLive e; e.v = nv; e.kb = j; e.row = tb.row_id[j]; Lv[(size_t)wl * VIT_LIST_MAX + cnt[wl][0]] = e; } ++cnt[wl][0]; }
+        if (nu >= thr) { if (cnt[wl][1] < VIT_LIST_MAX) { VitLive e; e.v = nu; e.kb = j; e.row = tb.row_id[j]; Lu[(size_t)wl * VIT_LIST_MAX + cnt[wl][1]] = e; } ++cnt[wl][1]; }
+      }
+      for (int q = 0; q < n_cand[t]; ++q) lpv[cand_bin[(size_t)t * g.kmax + q]] = tb.lt0;
+    }
+    const int lp_ = (int)((T - 1) & 1);
+    for (int j = 0; j < npb; ++j) { V[(size_t)lp_ * npb + j].x = Vv[(size_t)lp_ * VP + VIT_HW + j]; V[(size_t)lp_ * npb + j].y = Vu[(size_t)lp_ * VP + VIT_HW + j]; }
+    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps; unvoiced scans by half-width 1/5/25: %ld %ld %ld\n", listed, skipped, half_hist[0], half_hist[1], half_hist[2]);
+  } else {
   for (int64_t t = 1; t < T; ++t) {
     const cf64* Vc = V.data() + (size_t)((t - 1) & 1) * npb;
     cf64* Vn = V.data() + (size_t)(t & 1) * npb;
@@ -202,6 +263,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
       vit_step_bin(v, j, Vc, tb.lt_rows.data(), row_ofs.data(), lpv[j], lp_unv[t], kstar, vmax, &Vn[j],
                    ptr.data() + (size_t)t * 2 * npb);
     for (int c = 0; c < n_cand[t]; ++c) lpv[cand_bin[(size_t)t * g.kmax + c]] = tb.lt0;
+  }
   }
   int s; double m;
   argmax(V.data() + (size_t)((T - 1) & 1) * npb, &s, &m);
