@@ -39,6 +39,7 @@ struct VitParams {
   float* f0;                    // [frames]
   float* voiced_flag;           // [frames]
   int32_t lt_in_smem;
+  int32_t ptr_stride, ptr_uoff;   // back-pointer row layout: [voiced | unvoiced at ptr_uoff], row stride
   double lt_max;                // largest banded table entry
   const double* gap1;           // [n_warps] narrow-band gaps (fast path), see vit3_pick_half
   const double* gap5;
@@ -577,7 +578,7 @@ __global__ void k_pyin_backtrack(const VitParams p) {
     const bool voiced = s < p.npb;
     p.f0[f0 + t] = voiced ? (float)p.freqs[s] : 0.f;
     p.voiced_flag[f0 + t] = voiced ? 1.f : 0.f;
-    if (t > 0) s = p.ptr[(size_t)(f0 + t) * (2 * p.npb) + s];
+    if (t > 0) s = p.ptr[(size_t)(f0 + t) * p.ptr_stride + (s < p.npb ? s : s - p.npb + p.ptr_uoff)];
   }
 }
 

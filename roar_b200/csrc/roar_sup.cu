@@ -226,8 +226,10 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
   // ---- K2 / K3 tables
   {
     PyinTables t = make_pyin_tables(*cfg, g);
+    std::vector<double> lt_up = t.lt_rows;              // + one all-zero row for the fast Viterbi's sentinel sources
+    lt_up.resize(lt_up.size() + 2 * (size_t)g.tw, 0.0);
     UP(t.thresholds, d_thr) UP(t.beta_probs, d_beta) UP(t.beta_cum, d_beta_cum)
-    UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(t.lt_rows, d_lt_rows) UP(t.row_id, d_row_id)
+    UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(lt_up, d_lt_rows) UP(t.row_id, d_row_id)
     UP(t.freqs, d_freqs) UP(t.gap1, d_gap1) UP(t.gap5, d_gap5)
     h->n_rows = t.n_rows; h->lt0 = t.lt0; h->lt_max = t.lt_max; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
     // K2a tiling: frames per tile chosen for (i) two CTAs per SM, (ii) little block overhead
@@ -275,10 +277,10 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
     // fast path: the reference geometry (transition width 51), row ids in 6 bits
     h->vit3_smem = sizeof(Vit3Shared);
-    const char* env_gen = getenv("ROAR_SUP_VITERBI_GENERIC");
+    // ROAR_SUP_VITERBI=generic forces the any-geometry kernel (tests compare the two)
+    const char* env_v = getenv("ROAR_SUP_VITERBI");
     h->vit_fast = (g.tw == VIT_TW && t.n_rows + 1 <= VIT_ROWS_MAX && g.npb <= VIT_NPB_MAX && g.kmax <= VIT_KMAX_MAX &&
-                   h->vit3_smem <= h->max_smem &&
-                   !(env_gen && env_gen[0] == '1')) ? 1 : 0;
+                   h->vit3_smem <= h->max_smem && !(env_v && env_v[0] == 'g')) ? 1 : 0;
     if (h->vit_fast)
       CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi51, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit3_smem));
   }
@@ -365,7 +367,8 @@ static PyinWs pyin_ws_layout(const roar_sup_handle* h, int32_t n_utts, int64_t f
   w.cand_lp = (double*)take(sizeof(double) * (size_t)frames * g.kmax);
   w.cand_bin = (uint16_t*)take(sizeof(uint16_t) * (size_t)frames * g.kmax);
   w.energy = (float*)take(sizeof(float) * (size_t)frames * (g.max_period + 1));
-  size_t a = sizeof(double) * (size_t)frames * g.n_lags, b = sizeof(uint16_t) * (size_t)frames * 2 * g.npb;
+  size_t a = sizeof(double) * (size_t)frames * g.n_lags;
+  size_t b = sizeof(uint16_t) * (size_t)frames * 2 * g.npb;
   w.big = (double*)take(a > b ? a : b);
   w.total = o;
   return w;
@@ -442,6 +445,7 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
   v.cand_bin = w.cand_bin; v.cand_lp = w.cand_lp; v.n_cand = w.n_cand; v.lp_unvoiced = w.lp_unv;
   v.ptr = (uint16_t*)w.big; v.last_state = w.last_state; v.freqs = h->d_freqs; v.f0 = d_f0; v.voiced_flag = d_vflag;
   v.lt_in_smem = h->lt_in_smem; v.lt_max = h->lt_max; v.gap1 = h->d_gap1; v.gap5 = h->d_gap5;
+  v.ptr_stride = 2 * g.npb; v.ptr_uoff = g.npb;
   if (h->vit_fast) {
     LAUNCH(h, ROAR_K_VITERBI, st, (k_pyin_viterbi51<<<n_utts, h->vit_threads, h->vit3_smem, st>>>(v)));
   } else if (h->vit_threads <= 640) {

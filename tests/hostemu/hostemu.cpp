@@ -192,8 +192,10 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
   for (int c = 0; c < n_cand[0]; ++c) lpv[cand_bin[c]] = cand_lp[c];
   for (int j = 0; j < npb; ++j) { V[j].x = lpv[j] + tb.li_voiced; V[j].y = lp_unv[0] + tb.li_unvoiced; }
   for (int c = 0; c < n_cand[0]; ++c) lpv[cand_bin[c]] = tb.lt0;
-  const bool fast = g.tw == VIT_TW && tb.n_rows + 1 <= 64 && !getenv("ROAR_SUP_VITERBI_GENERIC");
-  if (fast) {
+  const char* env_v = getenv("ROAR_SUP_VITERBI");
+  const bool geom_ok = g.tw == VIT_TW && tb.n_rows + 1 <= 64 && npb <= 608;
+  const int fast = !geom_ok || (env_v && env_v[0] == 'g') ? 0 : 1;
+  if (fast == 1) {
     // fast path (k_pyin_viterbi51): padded V rows, live lists, dominance skipping
     const int VP = npb + 2 * VIT_HW;
     std::vector<double> Vv(2 * (size_t)VP, VIT_NEG), Vu(2 * (size_t)VP, VIT_NEG);

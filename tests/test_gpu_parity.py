@@ -171,6 +171,40 @@ def test_pyin_silence_tone_and_short(ex):
     assert np.abs(1200 * np.log2(mid / 220.0)).max() < 10.0
 
 
+def test_pyin_fast_viterbi_equals_generic_kernel(c1, monkeypatch):
+    """Pruned (default) vs exhaustive Viterbi kernel: identical f0 / flags on every frame."""
+    from roar_b200.config import SupConfig
+    from roar_b200.extractor import SupDataExtractor
+    man, wavs = c1
+    rng = np.random.default_rng(11)
+    wavs = list(wavs[:24]) + [(0.05 * rng.standard_normal(30000)).astype(np.float32),
+                              np.clip(4.0 * wavs[0], -0.9, 0.9).astype(np.float32)]
+    monkeypatch.delenv("ROAR_SUP_VITERBI", raising=False)
+    fast = SupDataExtractor(SupConfig(highfreq=8000.0))
+    monkeypatch.setenv("ROAR_SUP_VITERBI", "generic")
+    gen = SupDataExtractor(SupConfig(highfreq=8000.0))
+    a = fast.pyin(fast.pack(wavs))
+    b = gen.pyin(gen.pack(wavs))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+def test_pyin_44k_config4_vs_oracle():
+    """BASELINE config 4 geometry: 44.1 kHz, frame 2048 / hop 512 (min_period 21, max_period 675)."""
+    from oracle import pyin as opyin
+    from roar_b200 import synth
+    from roar_b200.config import SupConfig
+    from roar_b200.extractor import SupDataExtractor, split_frames
+    ex4 = SupDataExtractor(SupConfig(sample_rate=44100, n_fft=2048, win_length=2048, hop_length=512, highfreq=None))
+    wavs = [synth.synth_utterance(4, i, 44100 * 2 + 777 * i, 44100, i) for i in range(3)]
+    f0, vf, vp, fo = ex4.pyin(ex4.pack(wavs))
+    f0s, vfs, vps = split_frames(f0, fo), split_frames(vf, fo), split_frames(vp, fo)
+    for i, w in enumerate(wavs):
+        of0, ovf, ovp = opyin.pyin(w, FMIN, FMAX, sr=44100, frame_length=2048, fill_na=0.0)
+        flags_ok, cents, dvp = _pyin_compare(f0s[i].cpu().numpy(), vfs[i].cpu().numpy(), vps[i].cpu().numpy(),
+                                             of0, ovf, ovp)
+        assert flags_ok.mean() >= 0.999 and (cents <= 1.0).mean() >= 0.999 and np.quantile(dvp, 0.999) <= 1e-4
+
+
 def test_prior_vs_reference_golden(ex, golden_dir):
     """Against the reference's own outputs.  The reference evaluates the formula with float32 gammaln
     (its values are off the exact ones by up to ~2e-3 relative, measured below per case), so on rows

@@ -97,6 +97,24 @@ def test_emu_pyin_44k_and_edge_inputs():
         assert np.array_equal(vf.astype(bool), ovf) and np.array_equal(f0, of0.astype(np.float32))
 
 
+def test_emu_viterbi_fast_path_equals_generic(monkeypatch):
+    """The pruned Viterbi (live lists, dominance skipping) must decode the same state sequence as the
+    kernel that scans every in-band source -- including octave jumps, clipping and pure noise."""
+    cfg = SupConfig(highfreq=8000.0)
+    rng = np.random.default_rng(7)
+    t = np.arange(22050) / 22050.0
+    jump = np.where(t < 0.5, np.sin(2 * np.pi * 110 * t), np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    wavs = [_wav(3, 30000), (0.05 * rng.standard_normal(20000)).astype(np.float32), jump,
+            np.clip(3.0 * _wav(4, 20000), -0.9, 0.9).astype(np.float32)]
+    for y in wavs:
+        monkeypatch.delenv("ROAR_SUP_VITERBI", raising=False)
+        fast = hostemu.pyin(cfg, y, 329)
+        monkeypatch.setenv("ROAR_SUP_VITERBI", "generic")
+        gen = hostemu.pyin(cfg, y, 329)
+        assert np.array_equal(fast[4], gen[4])
+        assert np.array_equal(fast[0], gen[0]) and np.array_equal(fast[1], gen[1])
+
+
 def test_emu_prior(golden_dir):
     g = np.load(os.path.join(golden_dir, "prior_ref.npz"))
     for k in ("p_7_13", "p_100_560", "p_1_4", "p_2_9"):
