@@ -177,35 +177,47 @@ HD int energy_span(const PyinParams& p) { return (ENERGY_FT - 1) * p.hop + p.W +
 // stage the tile's squared samples (zero outside the utterance; librosa center=True, pad_mode="constant")
 HD void pyin_energy_stage(const PyinParams& p, const float* y, int L, int64_t q0, int n, float* sq, int tid,
                           int nthr) {
-  for (int i = tid; i < n; i += nthr) {
-    const int64_t q = q0 + i;
-    const float v = (q >= 0 && q < L) ? y[q] : 0.f;
-    sq[epad(i, p.hop)] = f32_mul(v, v);
+  const int hop = p.hop;
+  for (int s0 = 0, sg = 0; s0 < n; s0 += hop, ++sg) {
+    const int len = n - s0 < hop ? n - s0 : hop;
+    float* dst = sq + (size_t)sg * (hop + 1);
+    for (int i = tid; i < len; i += nthr) {
+      const int64_t q = q0 + s0 + i;
+      const float v = (q >= 0 && q < L) ? y[q] : 0.f;
+      dst[i] = f32_mul(v, v);
+    }
   }
 }
-// walks the epad layout sample by sample without dividing: `left` samples remain before the pad slot
-struct EpadWalk {
-  const float* p; int left, hop;
-  HD EpadWalk(const float* sq, int i, int hop_) : p(sq + epad(i, hop_)), left(hop_ - i % hop_), hop(hop_) {}
-  HD float next() {
-    const float v = *p++;
-    if (--left == 0) { ++p; left = hop; }
-    return v;
-  }
-};
-// one frame's chain; E = &energy[frame], rows `stride` floats apart (frame-contiguous rows)
+// one frame's chain; E = &energy[frame], rows `stride` floats apart (frame-contiguous rows).
+// The epad layout is contiguous inside a hop-sized segment, so the chain is walked run by run:
+// plain unit-stride inner loops, no per-sample index arithmetic.
 HD void pyin_energy_frame(const PyinParams& p, const float* sq, int f, float* E, size_t stride) {
-  const int base = f * p.hop;
+  const int hop = p.hop, seg = hop + 1;
   float cs = 0.f, cs2 = 0.f;
-  EpadWalk hi(sq, base, p.hop), lo(sq, base, p.hop);
-  for (int n = 0; n < p.W; ++n) cs = f32_add(cs, hi.next());
-  for (int tau = 0; tau <= p.max_period; ++tau) {
-    cs = f32_add(cs, hi.next());
-    cs2 = f32_add(cs2, lo.next());
-    float e = f32_sub(cs, cs2);
-    if (fabsf(e) < 1e-6f) e = 0.f;
-    *E = e;
-    E += stride;
+  // phase A: n = 0 .. W-1
+  for (int n0 = 0; n0 < p.W; n0 += hop) {
+    const float* ph = sq + (size_t)(f + n0 / hop) * seg;
+    const int len = p.W - n0 < hop ? p.W - n0 : hop;
+    for (int i = 0; i < len; ++i) cs = f32_add(cs, ph[i]);
+  }
+  // phase C: tau = 0 .. max_period; hi stream at sample W + tau, lo stream at sample tau
+  int tau = 0;
+  while (tau <= p.max_period) {
+    const int nh = p.W + tau, nl = tau;
+    const float* ph = sq + (size_t)(f + nh / hop) * seg + nh % hop;
+    const float* pl = sq + (size_t)(f + nl / hop) * seg + nl % hop;
+    int len = p.max_period + 1 - tau;
+    if (hop - nh % hop < len) len = hop - nh % hop;
+    if (hop - nl % hop < len) len = hop - nl % hop;
+    for (int i = 0; i < len; ++i) {
+      cs = f32_add(cs, ph[i]);
+      cs2 = f32_add(cs2, pl[i]);
+      float e = f32_sub(cs, cs2);
+      if (fabsf(e) < 1e-6f) e = 0.f;
+      *E = e;
+      E += stride;
+    }
+    tau += len;
   }
 }
 
@@ -314,13 +326,13 @@ struct ProbSmem {
   double* x;          // [n_lags]
   double* prob;       // [kmax]
   uint16_t* tr;       // [kmax] trough lag indices (increasing)
-  uint16_t* sorted;   // [kmax] trough ranks ordered by (c_r, r)
+  uint16_t* sorted;   // [kmax] active troughs (c_r < n_thr) in lag order
   int16_t* bin;       // [kmax]
   uint8_t* cr;        // [kmax] first threshold index the trough is below (n_thr = never)
   int32_t* cnt;       // [36]
   double* red;        // [32]
-  int32_t* carry;     // [n_thr] troughs of earlier chunks per first-threshold index
   uint8_t* live;      // [kmax]
+  int32_t* hist;      // [2 * n_thr] per-threshold counts of active troughs: all / already-processed chunks
 };
 HD size_t prob_smem_carve(const PyinParams& p, unsigned char* base, ProbSmem* s) {
   size_t o = 0;
@@ -329,9 +341,9 @@ HD size_t prob_smem_carve(const PyinParams& p, unsigned char* base, ProbSmem* s)
   CARVE(prob, double, p.kmax)
   CARVE(red, double, 32)
   CARVE(tr, uint16_t, p.kmax)
-  CARVE(sorted, uint16_t, (p.kmax > 2 * p.n_thr ? p.kmax : 2 * p.n_thr) + 2)   // also n_all[n_thr] ints
-  CARVE(carry, int32_t, p.n_thr)
+  CARVE(sorted, uint16_t, p.kmax + 2)
   CARVE(live, uint8_t, p.kmax)
+  CARVE(hist, int32_t, 2 * p.n_thr)
   CARVE(bin, int16_t, p.kmax)
   CARVE(cr, uint8_t, p.kmax)
   CARVE(cnt, int32_t, 36)
@@ -392,12 +404,8 @@ HD void prob_phase4(const PyinParams& p, ProbSmem& s, int lane) {
   s.cnt[33] = bi;
 }
 
-// Threshold-beta / Boltzmann probabilities.  Lanes own troughs (chunks of 32 in lag order); the loop
-// over the thresholds c is warp-uniform.  n_c = #{r : c_r <= c} is uniform; pos(r, c) =
-// #{r' < r : c_r' <= c} advances by the number of earlier troughs whose first threshold is c, which
-// is a ballot + popcount inside the chunk plus a per-threshold carry from the previous chunks.
-//   probs_r = sum_{c >= c_r} (fact[n_c] * exp(-lambda * pos)) * beta[c]   (+ no-trough bonus on the global min)
-// `hist` [n_thr] (ints) aliases s.sorted (unused otherwise).
+// Threshold-beta / Boltzmann probability of trough r is finished here: the no-trough bonus on the
+// global minimum, parabolic period refinement and pitch-bin quantisation.
 HD void prob_trough_finish(const PyinParams& p, ProbSmem& s, int r, double acc) {
   const int cr = s.cr[r];
   if (r == s.cnt[33]) acc += p.no_trough_prob * p.beta_cum[cr];
@@ -422,34 +430,32 @@ HD void prob_trough_finish(const PyinParams& p, ProbSmem& s, int r, double acc) 
   s.bin[r] = (int16_t)bin;
 }
 
-// n_all[c] = #{r : c_r <= c} over ALL troughs (kept in smem, [n_thr] ints, aliases s.sorted)
-HD void prob_phase5a(const PyinParams& p, ProbSmem& s, int lane) {
+// Only ACTIVE troughs (height below the last threshold, c_r < n_thr) take part in the threshold sums:
+// an inactive trough is never "below", so it adds nothing to n_c or to anybody's rank.  The active
+// troughs are compacted in lag order (s.sorted[0..Na)); for trough a
+//   probs_a = sum_{c = c_a .. n_thr-1} (fact[n_c] * exp(-lambda * pos(a, c))) * beta[c],
+//   n_c = #{a' : c_a' <= c},  pos(a, c) = #{a' < a : c_a' <= c},
+// accumulated in ascending c exactly like the dense formulation.  This is the sequential statement the
+// host harness runs; the kernel evaluates the same sums with ballots (lanes own active troughs).
+HD int prob_compact_active(const PyinParams& p, ProbSmem& s) {
   const int R = s.cnt[32];
-  int* n_all = reinterpret_cast<int*>(s.sorted);
-  for (int c = lane; c < p.n_thr; c += 32) {
-    int n = 0;
-    for (int r = 0; r < R; ++r) n += ((int)s.cr[r] <= c) ? 1 : 0;
-    n_all[c] = n;
-  }
+  int na = 0;
+  for (int r = 0; r < R; ++r) if ((int)s.cr[r] < p.n_thr) s.sorted[na++] = (uint16_t)r;
+  return na;
 }
-// one chunk of 32 troughs; `carry[c]` (ints, [n_thr], aliases s.bin's tail? no: own array s.carry)
-HD void prob_phase5b_lane(const PyinParams& p, ProbSmem& s, int base, int lane, const int* chunk_cr /*[32]*/) {
-  // reference formulation used by the host harness: identical arithmetic, ballot replaced by a scan
-  const int R = s.cnt[32];
-  const int r = base + lane;
-  if (r >= R) return;
-  const int* n_all = reinterpret_cast<const int*>(s.sorted);
-  const int cr = s.cr[r];
+HD double prob_active_sum(const PyinParams& p, const ProbSmem& s, int na, int a) {
+  const int cra = s.cr[s.sorted[a]];
   double acc = 0.0;
-  int pos = 0;
-  // earlier chunks: every trough r' < base counts when c_r' <= c
-  for (int c = 0; c < p.n_thr; ++c) {
-    int inc = s.carry[c];
-    for (int l = 0; l < lane; ++l) inc += (chunk_cr[l] == c) ? 1 : 0;
-    pos += inc;
-    if (c >= cr) acc += (p.boltz_fact[n_all[c]] * p.boltz_exp[pos]) * p.beta_probs[c];
+  for (int c = cra; c < p.n_thr; ++c) {
+    int n = 0, pos = 0;
+    for (int q = 0; q < na; ++q) {
+      const bool below = (int)s.cr[s.sorted[q]] <= c;
+      n += below ? 1 : 0;
+      pos += (below && q < a) ? 1 : 0;
+    }
+    acc += (p.boltz_fact[n] * p.boltz_exp[pos]) * p.beta_probs[c];
   }
-  prob_trough_finish(p, s, r, acc);
+  return acc;
 }
 
 // live = survives NumPy's last-write-wins scatter: no later trough with a non-zero probability
@@ -499,10 +505,12 @@ HD void prob_phase6b(const PyinParams& p, ProbSmem& s, int64_t frame, int lane) 
 }
 
 #ifdef __CUDACC__
-// one warp per tile of 32 consecutive frames of one utterance, one lane per frame
-__global__ void __launch_bounds__(32) k_pyin_energy(const PyinParams p) {
+// one CTA per tile of 32 consecutive frames of one utterance: 128 threads stage the squared samples,
+// then warp 0 runs the 32 serial chains (one lane per frame)
+constexpr int ENERGY_THREADS = 128;
+__global__ void __launch_bounds__(ENERGY_THREADS) k_pyin_energy(const PyinParams p) {
   extern __shared__ __align__(16) float e_smem[];
-  const int tile = blockIdx.x, lane = threadIdx.x;
+  const int tile = blockIdx.x, tid = threadIdx.x;
   if (tile >= p.etile_off[p.n_utts]) return;
   int lo = 0, hi = p.n_utts;
   while (hi - lo > 1) {
@@ -514,10 +522,10 @@ __global__ void __launch_bounds__(32) k_pyin_energy(const PyinParams p) {
   const int nf = T - t0 < ENERGY_FT ? T - t0 : ENERGY_FT;
   const int n = (nf - 1) * p.hop + p.W + p.max_period + 1;
   pyin_energy_stage(p, p.audio + p.sample_off[lo], p.sample_len[lo], (int64_t)t0 * p.hop - p.F / 2, n, e_smem,
-                    lane, 32);
-  __syncwarp();
-  if (lane < nf)
-    pyin_energy_frame(p, e_smem, lane, p.energy + (p.frame_off[lo] + t0 + lane), (size_t)p.total_frames);
+                    tid, ENERGY_THREADS);
+  __syncthreads();
+  if (tid < nf)
+    pyin_energy_frame(p, e_smem, tid, p.energy + (p.frame_off[lo] + t0 + tid), (size_t)p.total_frames);
 }
 
 constexpr int CMND_THREADS = 256;   // 8 warps, each takes every 8th autocorrelation chunk
@@ -561,7 +569,12 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
   prob_smem_carve(p, smem_raw + (size_t)warp * per, &s);
   // thresholds staged once per CTA behind the per-warp areas
   double* thr = (double*)(smem_raw + (size_t)wpb * per);
+  double* beta = thr + p.n_thr + 2;
+  double* bexp = beta + p.n_thr + 2;
+  double* bfact = bexp + p.kmax + 2;
   for (int i = threadIdx.x; i <= p.n_thr; i += blockDim.x) thr[i] = p.thresholds[i];
+  for (int i = threadIdx.x; i < p.n_thr; i += blockDim.x) beta[i] = p.beta_probs[i];
+  for (int i = threadIdx.x; i <= p.kmax; i += blockDim.x) { bexp[i] = p.boltz_exp[i]; bfact[i] = p.boltz_fact[i]; }
   __syncthreads();
   for (int64_t frame = (int64_t)blockIdx.x * wpb + warp; frame < p.total_frames;
        frame += (int64_t)gridDim.x * wpb) {
@@ -570,26 +583,52 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
     prob_phase2(p, s, lane); __syncwarp();
     prob_phase3(p, s, lane, thr); __syncwarp();
     prob_phase4(p, s, lane); __syncwarp();
-    prob_phase5a(p, s, lane);
-    for (int c = lane; c < p.n_thr; c += 32) s.carry[c] = 0;
-    __syncwarp();
     {
       const int R = s.cnt[32];
-      const int* n_all = reinterpret_cast<const int*>(s.sorted);
-      const unsigned lt_mask = (1u << lane) - 1u;
+      // compact the active troughs in lag order
+      int na = 0;
       for (int base = 0; base < R; base += 32) {
         const int r = base + lane;
-        const int cr = r < R ? (int)s.cr[r] : 0x7fff;
+        const bool act = r < R && (int)s.cr[r] < p.n_thr;
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (act) s.sorted[na + __popc(m & ((1u << lane) - 1u))] = (uint16_t)r;
+        na += __popc(m);
+      }
+      __syncwarp();
+      // inactive troughs: probability 0 (the global minimum still gets the no-trough bonus)
+      for (int r = lane; r < R; r += 32) if ((int)s.cr[r] >= p.n_thr) prob_trough_finish(p, s, r, 0.0);
+      const unsigned lt_mask = (1u << lane) - 1u;
+      // hist[c] = #{active a : c_a == c} (n_c is its running sum); carry[c] = the same over the
+      // chunks already processed (ranks of later chunks start from it)
+      int* hist = s.hist;
+      int* carry = s.hist + p.n_thr;
+      for (int c = lane; c < 2 * p.n_thr; c += 32) hist[c] = 0;
+      __syncwarp();
+      int cmin = 0x7fff;
+      for (int a = lane; a < na; a += 32) {
+        const int cr = (int)s.cr[s.sorted[a]];
+        atomicAdd(&hist[cr], 1);
+        cmin = cr < cmin ? cr : cmin;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const int x = __shfl_xor_sync(0xffffffffu, cmin, o); cmin = x < cmin ? x : cmin; }
+      __syncwarp();
+      for (int base = 0; base < na; base += 32) {
+        const int a = base + lane;
+        const int r = a < na ? (int)s.sorted[a] : -1;
+        const int cr = r >= 0 ? (int)s.cr[r] : 0x7fff;
+        const bool more = base + 32 < na;
         double acc = 0.0;
-        int pos = 0;
-        for (int c = 0; c < p.n_thr; ++c) {
+        int pos = 0, n = 0;
+        for (int c = cmin; c < p.n_thr; ++c) {
           const unsigned m = __ballot_sync(0xffffffffu, cr == c);
-          const int carry = s.carry[c];
-          pos += carry + __popc(m & lt_mask);
-          if (c >= cr) acc += (p.boltz_fact[n_all[c]] * p.boltz_exp[pos]) * p.beta_probs[c];
-          if (lane == 0 && m) s.carry[c] = carry + __popc(m);
+          const int cy = carry[c];
+          n += hist[c];
+          pos += cy + __popc(m & lt_mask);
+          if (c >= cr) acc += (bfact[n] * bexp[pos]) * beta[c];
+          if (more && lane == 0 && m) carry[c] = cy + __popc(m);
         }
-        if (r < R) prob_trough_finish(p, s, r, acc);
+        if (r >= 0) prob_trough_finish(p, s, r, acc);
         __syncwarp();
       }
     }

@@ -257,7 +257,7 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     }
     PyinParams pp = pyin_params_base(h);
     h->cmnd_smem = cmnd_smem_carve(pp, nullptr, nullptr);
-    h->prob_smem = prob_smem_carve(pp, nullptr, nullptr) * 8 + sizeof(double) * (g.n_thr + 2);
+    h->prob_smem = prob_smem_carve(pp, nullptr, nullptr) * 8 + sizeof(double) * (2 * (g.n_thr + 2) + 2 * (g.kmax + 2));
     if (h->cmnd_smem > h->max_smem || h->prob_smem > h->max_smem) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "pYIN tile does not fit in shared memory"); }
     CUDA_TRY(cudaFuncSetAttribute(k_pyin_cmnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cmnd_smem));
     h->energy_smem = sizeof(float) * (size_t)(epad(energy_span(pp), g.ph) + 4);
@@ -423,7 +423,7 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
   LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, p.FT, w.tile_off));
   const int64_t max_tiles = total_frames / p.FT + n_utts;
   LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, ENERGY_FT, w.etile_off));
-  LAUNCH(h, ROAR_K_PYIN_ENERGY, st, k_pyin_energy<<<(unsigned)(total_frames / ENERGY_FT + n_utts), 32, h->energy_smem, st>>>(p));
+  LAUNCH(h, ROAR_K_PYIN_ENERGY, st, k_pyin_energy<<<(unsigned)(total_frames / ENERGY_FT + n_utts), ENERGY_THREADS, h->energy_smem, st>>>(p));
   LAUNCH(h, ROAR_K_PYIN_CMND, st, k_pyin_cmnd<<<(unsigned)max_tiles, CMND_THREADS, h->cmnd_smem, st>>>(p));
   int64_t pb = (total_frames + 7) / 8;
   const int64_t cap = (int64_t)h->sm_count * 16;

@@ -154,16 +154,11 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
       for (int l = 0; l < 32; ++l) prob_phase2(p, s, l);
       for (int l = 0; l < 32; ++l) prob_phase3(p, s, l, tb.thresholds.data());
       for (int l = 0; l < 32; ++l) prob_phase4(p, s, l);
-      for (int l = 0; l < 32; ++l) prob_phase5a(p, s, l);
-      for (int c = 0; c < p.n_thr; ++c) s.carry[c] = 0;
       {
         const int R = s.cnt[32];
-        for (int base = 0; base < R; base += 32) {
-          int chunk_cr[32];
-          for (int l = 0; l < 32; ++l) chunk_cr[l] = base + l < R ? (int)s.cr[base + l] : 0x7fff;
-          for (int l = 0; l < 32; ++l) prob_phase5b_lane(p, s, base, l, chunk_cr);
-          for (int l = 0; l < 32; ++l) if (chunk_cr[l] < p.n_thr) s.carry[chunk_cr[l]] += 1;
-        }
+        const int na = prob_compact_active(p, s);
+        for (int r = 0; r < R; ++r) if ((int)s.cr[r] >= p.n_thr) prob_trough_finish(p, s, r, 0.0);
+        for (int a = 0; a < na; ++a) prob_trough_finish(p, s, s.sorted[a], prob_active_sum(p, s, na, a));
       }
       for (int l = 0; l < 32; ++l) prob_phase6a(p, s, l);
       for (int l = 0; l < 32; ++l) prob_phase6b(p, s, fr, l);
