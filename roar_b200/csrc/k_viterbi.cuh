@@ -41,8 +41,6 @@ struct VitParams {
   int32_t lt_in_smem;
   int32_t ptr_stride, ptr_uoff;   // back-pointer row layout: [voiced | unvoiced at ptr_uoff], row stride
   double lt_max;                // largest banded table entry
-  const double* gap1;           // [n_warps] narrow-band gaps (fast path), see vit3_pick_half
-  const double* gap5;
 };
 
 struct VitBest { double v; int k; };
@@ -218,6 +216,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
 constexpr int VIT_TW = 51;
 constexpr int VIT_HW = 25;
 constexpr int VIT_LIST_MAX = 64;
+constexpr int VIT_CHAINS = 1;
 constexpr int VIT_RID_REGS = (VIT_TW + 4) / 5;   // 11
 constexpr double VIT_NEG = -1e308;
 
@@ -242,48 +241,34 @@ HD void vit_pack_rows(const uint16_t* row_id, int npb, int zero_row, int j, uint
 // same/swit: best offers for the destination of the same / the other voicing; d_* = winning d.
 HD void vit_band_scan(const double* Vp, const cf64* lt2, const uint32_t* rid, double* same_b, int* same_d,
                       double* swit_b, int* swit_d) {
-  // three independent running maxima (sources 0-16, 17-33, 34-50) merged in source order with a strict
-  // compare: same first-index arg-max as one chain, three times the instruction-level parallelism
-  double b0[3], b1[3];
-  int d0[3], d1[3];
+  // VIT_CHAINS independent running maxima over consecutive source ranges, merged in source order with
+  // a strict compare: same first-index arg-max as one chain, more instruction-level parallelism
+  constexpr int NCH = VIT_CHAINS, PER = (VIT_TW + NCH - 1) / NCH;
+  double b0[NCH], b1[NCH];
+  int d0[NCH], d1[NCH];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { b0[c] = VIT_NEG; b1[c] = VIT_NEG; d0[c] = 0; d1[c] = 0; }
+  for (int c = 0; c < NCH; ++c) { b0[c] = VIT_NEG; b1[c] = VIT_NEG; d0[c] = 0; d1[c] = 0; }
 #pragma unroll
-  for (int q = 0; q < 17; ++q) {
+  for (int q = 0; q < PER; ++q) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int d = c * 17 + q;
-      const double v = Vp[d];
-      const uint32_t row = (rid[d / 5] >> (6 * (d % 5))) & 63u;
-      const cf64 e = lt2[row * VIT_TW + (2 * VIT_HW - d)];
-      const double s0 = v + e.x, s1 = v + e.y;
-      if (s0 > b0[c]) { b0[c] = s0; d0[c] = d; }
-      if (s1 > b1[c]) { b1[c] = s1; d1[c] = d; }
+    for (int c = 0; c < NCH; ++c) {
+      const int d = c * PER + q;
+      if (d < VIT_TW) {
+        const double v = Vp[d];
+        const uint32_t row = (rid[d / 5] >> (6 * (d % 5))) & 63u;
+        const cf64 e = lt2[row * VIT_TW + (2 * VIT_HW - d)];
+        const double s0 = v + e.x, s1 = v + e.y;
+        if (s0 > b0[c]) { b0[c] = s0; d0[c] = d; }
+        if (s1 > b1[c]) { b1[c] = s1; d1[c] = d; }
+      }
     }
   }
 #pragma unroll
-  for (int c = 1; c < 3; ++c) {
+  for (int c = 1; c < NCH; ++c) {
     if (b0[c] > b0[0]) { b0[0] = b0[c]; d0[0] = d0[c]; }
     if (b1[c] > b1[0]) { b1[0] = b1[c]; d1[0] = d1[c]; }
   }
   *same_b = b0[0]; *same_d = d0[0]; *swit_b = b1[0]; *swit_d = d1[0];
-}
-// the same over sources j-D .. j+D only (see the narrow-band rule in vit3_step_bin)
-template <int D>
-HD void vit_band_scan_narrow(const double* Vp, const cf64* lt2, const uint32_t* rid, double* same_b, int* same_d,
-                             double* swit_b, int* swit_d) {
-  double b0 = VIT_NEG, b1 = VIT_NEG;
-  int d0 = 0, d1 = 0;
-#pragma unroll
-  for (int d = VIT_HW - D; d <= VIT_HW + D; ++d) {
-    const double v = Vp[d];
-    const uint32_t row = (rid[d / 5] >> (6 * (d % 5))) & 63u;
-    const cf64 e = lt2[row * VIT_TW + (2 * VIT_HW - d)];
-    const double s0 = v + e.x, s1 = v + e.y;
-    if (s0 > b0) { b0 = s0; d0 = d; }
-    if (s1 > b1) { b1 = s1; d1 = d; }
-  }
-  *same_b = b0; *same_d = d0; *swit_b = b1; *swit_d = d1;
 }
 
 // one live-list entry against destination bin j: `same` gets e.v + ls, `swit` gets e.v + lc
@@ -304,28 +289,11 @@ struct Vit3Step {
   const VitLive* Lu; int nu;
   double vmax; int kstar;      // first global arg-max of V[t-1]
   double vvmax;                // max over the voiced V[t-1] a destination of this warp can see in band
-  int u_half;                  // unvoiced band scan half-width for this warp: 25 (full), 5 or 1
   // tables
   const cf64* lt2;             // [n_rows+1][51] (ls, lc), last row zeros
   double lt0, lt_max;
   int npb;
 };
-
-// NARROW-BAND rule for the unvoiced scan of warp w (32 consecutive destination bins).  Let
-// delta = max(Vu over the bins of warps w-1, w, w+1) - min(Vu over the bins of warp w) and
-// G_D[w] = min over destinations j of w, in-band sources k with |k-j| > D and both table components of
-// (lt[j->j] - lt[k->j]) (host table, exact).  If delta < G_D[w] - 1e-6, every source farther than D
-// offers strictly less than the destination's own bin does (rounding moves either side by < 1e-10),
-// so scanning j-D .. j+D yields the same arg-max.  Flat stretches of Vu (most of an unvoiced passage,
-// and everything away from the candidates in a voiced one) need D = 1.
-HD int vit3_pick_half(double delta, double g1, double g5) {
-#ifndef VIT_NARROW_BAND
-  (void)delta; (void)g1; (void)g5; return VIT_HW;   // see DESIGN.md: per-warp narrowing lengthens the per-step critical path
-#endif
-  if (delta < g1 - 1e-6) return 1;
-  (void)g5;   // a half-width-5 tier was measured: it fires on < 1 % of the scans, not worth the code
-  return VIT_HW;
-}
 
 // new values and back-pointers of pitch bin j
 HD void vit3_step_bin(const Vit3Step& c, int j, const uint32_t* rid, double lp_v, double lp_u, double* out_v,
@@ -339,8 +307,7 @@ HD void vit3_step_bin(const Vit3Step& c, int j, const uint32_t* rid, double lp_v
   }
   if (c.nu > VIT_LIST_MAX) {
     double sb, wb; int sd, wd;
-    if (c.u_half == 1) vit_band_scan_narrow<1>(c.Vu + j, c.lt2, rid, &sb, &sd, &wb, &wd);
-    else vit_band_scan(c.Vu + j, c.lt2, rid, &sb, &sd, &wb, &wd);
+    vit_band_scan(c.Vu + j, c.lt2, rid, &sb, &sd, &wb, &wd);
     vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
     vit_offer(bv, wb, c.npb + j - VIT_HW + wd);
   } else {
@@ -384,17 +351,11 @@ HD double vit3_lower_bound(const Vit3Step& c, const uint16_t* row_id, double lp_
 #ifdef __CUDACC__
 // Warp reductions over NEGATIVE finite doubles with redux.sync: for negative values, larger value <=>
 // smaller (hi, lo) bit pattern as unsigned.  Every V of this HMM is < 0 (sums of logs of
-// probabilities), and the fillers are -1e308 (max) / -0.0 (min).
+// probabilities), and the fillers are -1e308.
 __device__ __forceinline__ double vit_warp_max(double v) {
   const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
   const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
   const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
-  return __hiloint2double((int)mhi, (int)mlo);
-}
-__device__ __forceinline__ double vit_warp_min(double v) {
-  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
-  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
   return __hiloint2double((int)mhi, (int)mlo);
 }
 // (max value, smallest index attaining it)
@@ -420,8 +381,7 @@ struct alignas(16) Vit3Shared {
   double clp[2][VIT_KMAX_MAX];               // its candidate list (log-prob, bin)
   VitLive Lv[3][VIT_LIST_MAX];               // live lists: slot t % 3
   VitLive Lu[3][VIT_LIST_MAX];
-  double wv[2][32], wvv[2][32], wumax[2][32], wumin[2][32];   // per-warp partials (= 32-bin segment stats)
-  double g1[32], g5[32];                     // narrow-band gaps per warp
+  double wv[2][32], wvv[2][32];              // per-warp partials (= 32-bin segment stats)
   int wk[2][32];
   int cnt[3][2];
   int pad_[2];
@@ -459,7 +419,6 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     for (int i = tid; i < VIT_TW; i += nthr) { cf64 z; z.x = 0.0; z.y = 0.0; s.lt2[n + i] = z; }
     for (int i = tid; i < npb; i += nthr) { s.rowid[i] = p.row_id[i]; s.lpv[0][i] = p.lt0; s.lpv[1][i] = p.lt0; }
     for (int i = tid; i < VIT_VP_MAX; i += nthr) { s.Vv[0][i] = VIT_NEG; s.Vv[1][i] = VIT_NEG; s.Vu[0][i] = VIT_NEG; s.Vu[1][i] = VIT_NEG; }
-    if (tid < 32) { s.g1[tid] = tid < nwarp ? p.gap1[tid] : 0.0; s.g5[tid] = tid < nwarp ? p.gap5[tid] : 0.0; }
     if (tid < 6) (&s.cnt[0][0])[tid] = tid < 2 ? VIT_LIST_MAX + 1 : 0;   // time 0: scan everything
   }
   const int j = tid;
@@ -470,13 +429,13 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
   int nc_cur = p.n_cand[f0];
   if (tid < nc_cur) s.lpv[0][p.cand_bin[(size_t)f0 * kmax + tid]] = p.cand_lp[(size_t)f0 * kmax + tid];
   __syncthreads();
-  double bestv = VIT_NEG, vvb = VIT_NEG, umx = VIT_NEG, umn = -0.0; int bestk = 0x7fffffff;
+  double bestv = VIT_NEG, vvb = VIT_NEG; int bestk = 0x7fffffff;
   if (j < npb) {
     const double vv = s.lpv[0][j] + p.li_voiced;
     const double vu = p.lp_unvoiced[f0] + p.li_unvoiced;
     s.lpv[0][j] = p.lt0;
     s.Vv[0][VIT_HW + j] = vv; s.Vu[0][VIT_HW + j] = vu;
-    bestv = vv; bestk = j; vvb = vv; umx = vu; umn = vu;
+    bestv = vv; bestk = j; vvb = vv;
     if (vu > bestv) { bestv = vu; bestk = npb + j; }
   }
   double lp_u_next = 0.0;
@@ -490,8 +449,8 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     }
   }
   vit_warp_argmax_neg(bestv, bestk);
-  vvb = vit_warp_max(vvb); umx = vit_warp_max(umx); umn = vit_warp_min(umn);
-  if (lane == 0) { s.wv[0][warp] = bestv; s.wk[0][warp] = bestk; s.wvv[0][warp] = vvb; s.wumax[0][warp] = umx; s.wumin[0][warp] = umn; }
+  vvb = vit_warp_max(vvb);
+  if (lane == 0) { s.wv[0][warp] = bestv; s.wk[0][warp] = bestk; s.wvv[0][warp] = vvb; }
   __syncthreads();
 
   uint16_t* pr = p.ptr + (size_t)(f0 + 1) * (2 * npb);
@@ -505,11 +464,10 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       vit_warp_argmax_neg(vmax, kstar);
       c.vmax = vmax; c.kstar = kstar;
       // sources in band of this warp's destinations live in the 32-bin segments of warps w-1, w, w+1
-      double seg = s.wvv[rp][warp], um = s.wumax[rp][warp];
-      if (warp > 0) { const double x = s.wvv[rp][warp - 1], y = s.wumax[rp][warp - 1]; if (x > seg) seg = x; if (y > um) um = y; }
-      if (warp + 1 < nwarp) { const double x = s.wvv[rp][warp + 1], y = s.wumax[rp][warp + 1]; if (x > seg) seg = x; if (y > um) um = y; }
+      double seg = s.wvv[rp][warp];
+      if (warp > 0) { const double x = s.wvv[rp][warp - 1]; if (x > seg) seg = x; }
+      if (warp + 1 < nwarp) { const double x = s.wvv[rp][warp + 1]; if (x > seg) seg = x; }
       c.vvmax = seg;
-      c.u_half = vit3_pick_half(um - s.wumin[rp][warp], s.g1[warp], s.g5[warp]);
     }
     c.Vv = s.Vv[rp]; c.Vu = s.Vu[rp];
     c.Lv = s.Lv[rl]; c.Lu = s.Lu[rl];
@@ -534,7 +492,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
         nb_lp = p.cand_lp[(size_t)(f0 + t + 1) * kmax + tid];
       }
     }
-    bestv = VIT_NEG; bestk = 0x7fffffff; vvb = VIT_NEG; umx = VIT_NEG; umn = -0.0;
+    bestv = VIT_NEG; bestk = 0x7fffffff; vvb = VIT_NEG;
     bool live_v = false, live_u = false;
     double nv = VIT_NEG, nu = VIT_NEG;
     if (j < npb) {
@@ -543,7 +501,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       s.lpv[wp][j] = p.lt0;
       s.Vv[wp][VIT_HW + j] = nv; s.Vu[wp][VIT_HW + j] = nu;
       pr[j] = (uint16_t)av; pr[npb + j] = (uint16_t)au;
-      bestv = nv; bestk = j; vvb = nv; umx = nu; umn = nu;
+      bestv = nv; bestk = j; vvb = nv;
       if (nu > bestv) { bestv = nu; bestk = npb + j; }
       live_v = nv >= thr; live_u = nu >= thr;
     }
@@ -553,8 +511,8 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     if (tid < nc_next) { s.lpv[wp ^ 1][nb_bin] = nb_lp; s.cbin[wp ^ 1][tid] = (uint16_t)nb_bin; s.clp[wp ^ 1][tid] = nb_lp; }
     nc_cur = nc_next;
     vit_warp_argmax_neg(bestv, bestk);
-    vvb = vit_warp_max(vvb); umx = vit_warp_max(umx); umn = vit_warp_min(umn);
-    if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; s.wumax[wp][warp] = umx; s.wumin[wp][warp] = umn; }
+    vvb = vit_warp_max(vvb);
+    if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; }
     __syncthreads();
   }
   if (warp == 0) {

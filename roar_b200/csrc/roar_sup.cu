@@ -46,7 +46,6 @@ struct roar_sup_handle {
   int pyin_FT = 15, pyin_BL = 0, pyin_nb = 0, pyin_ngroups = 0, pyin_ylen = 0; size_t cmnd_smem = 0, prob_smem = 0, energy_smem = 0;
   // K3
   double* d_lt_rows = nullptr; uint16_t* d_row_id = nullptr; double* d_freqs = nullptr;
-  double *d_gap1 = nullptr, *d_gap5 = nullptr;
   int n_rows = 0; double lt0 = 0, lt_max = 0, li_v = 0, li_u = 0;
   int vit_threads = 0; size_t vit_smem = 0; int lt_in_smem = 1;
   int vit_fast = 0; size_t vit3_smem = 0;
@@ -230,7 +229,7 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     lt_up.resize(lt_up.size() + 2 * (size_t)g.tw, 0.0);
     UP(t.thresholds, d_thr) UP(t.beta_probs, d_beta) UP(t.beta_cum, d_beta_cum)
     UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(lt_up, d_lt_rows) UP(t.row_id, d_row_id)
-    UP(t.freqs, d_freqs) UP(t.gap1, d_gap1) UP(t.gap5, d_gap5)
+    UP(t.freqs, d_freqs)
     h->n_rows = t.n_rows; h->lt0 = t.lt0; h->lt_max = t.lt_max; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
     // K2a tiling: frames per tile chosen for (i) two CTAs per SM, (ii) little block overhead
     // (a tile of ft frames computes ft + nb - 1 blocks), (iii) a chunk count that fills the 8 warps
@@ -444,7 +443,7 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
   v.lt_rows = h->d_lt_rows; v.row_id = h->d_row_id; v.lt0 = h->lt0; v.li_voiced = h->li_v; v.li_unvoiced = h->li_u;
   v.cand_bin = w.cand_bin; v.cand_lp = w.cand_lp; v.n_cand = w.n_cand; v.lp_unvoiced = w.lp_unv;
   v.ptr = (uint16_t*)w.big; v.last_state = w.last_state; v.freqs = h->d_freqs; v.f0 = d_f0; v.voiced_flag = d_vflag;
-  v.lt_in_smem = h->lt_in_smem; v.lt_max = h->lt_max; v.gap1 = h->d_gap1; v.gap5 = h->d_gap5;
+  v.lt_in_smem = h->lt_in_smem; v.lt_max = h->lt_max;
   v.ptr_stride = 2 * g.npb; v.ptr_uoff = g.npb;
   if (h->vit_fast) {
     LAUNCH(h, ROAR_K_VITERBI, st, (k_pyin_viterbi51<<<n_utts, h->vit_threads, h->vit3_smem, st>>>(v)));

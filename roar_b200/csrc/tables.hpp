@@ -234,7 +234,6 @@ struct PyinTables {
   int n_rows = 0;
   double lt0 = 0;                   // log(0 + tiny): every out-of-band transition
   double lt_max = 0;                // largest entry of lt_rows
-  std::vector<double> gap1, gap5;   // [ceil(npb/32)] narrow-band gaps of the fast Viterbi (k_viterbi.cuh)
   double li_voiced = 0, li_unvoiced = 0;  // log(p_init + tiny)
 };
 
@@ -342,26 +341,6 @@ inline PyinTables make_pyin_tables(const roar_sup_config& c, const Geometry& g) 
   t.n_rows = (int)seen.size();
   t.lt_max = t.lt0;
   for (double v : t.lt_rows) if (v > t.lt_max) t.lt_max = v;
-  // narrow-band gaps per 32-bin destination segment: min over destinations j, in-band sources k with
-  // |k - j| > D and both components of (lt[j->j] - lt[k->j])
-  {
-    const int nw = (n + 31) / 32;
-    t.gap1.assign(nw, -1.0); t.gap5.assign(nw, -1.0);
-    for (int w = 0; w < nw; ++w)
-      for (int pass = 0; pass < 2; ++pass) {
-        const int D = pass == 0 ? 1 : 5;
-        double gmin = 1e300;
-        for (int j = w * 32; j < w * 32 + 32 && j < n; ++j) {
-          const double* self = &t.lt_rows[((size_t)t.row_id[j] * tw + hw) * 2];
-          for (int k = j - hw; k <= j + hw; ++k) {
-            if (k < 0 || k >= n || (k >= j - D && k <= j + D)) continue;
-            const double* e = &t.lt_rows[((size_t)t.row_id[k] * tw + (j - k + hw)) * 2];
-            for (int c = 0; c < 2; ++c) gmin = std::min(gmin, self[c] - e[c]);
-          }
-        }
-        (pass == 0 ? t.gap1 : t.gap5)[w] = gmin > 0 && gmin < 1e299 ? gmin : -1.0;
-      }
-  }
   t.li_voiced = std::log(0.0 + kTiny64);
   t.li_unvoiced = std::log(1.0 / n + kTiny64);
   return t;

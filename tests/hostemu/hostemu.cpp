@@ -202,7 +202,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     std::vector<uint32_t> rid((size_t)npb * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) vit_pack_rows(tb.row_id.data(), npb, tb.n_rows, j, rid.data() + (size_t)j * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) { Vv[VIT_HW + j] = V[j].x; Vu[VIT_HW + j] = V[j].y; }
-    long skipped = 0, listed = 0, half_hist[3] = {0, 0, 0};
+    long skipped = 0, listed = 0;
     for (int64_t t = 1; t < T; ++t) {
       const int rp = (int)((t - 1) & 1), wp = (int)(t & 1), rl = (int)((t - 1) % 3), wl = (int)(t % 3), zl = (int)((t + 1) % 3);
       Vit3Step c;
@@ -225,18 +225,12 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
       for (int q = 0; q < n_cand[t]; ++q) lpv[cand_bin[(size_t)t * g.kmax + q]] = cand_lp[(size_t)t * g.kmax + q];
       for (int j = 0; j < npb; ++j) {
         double nv, nu; int av, au;
-        {   // the kernel's per-warp statistics over the 32-bin segments w-1, w, w+1
+        {   // the kernel's per-warp bound: voiced maximum over the 32-bin segments w-1, w, w+1
           const int w = j / 32, nw = (npb + 31) / 32;
-          double seg = -1e308, um = -1e308, umin = 0.0;
+          double seg = -1e308;
           for (int ww = (w > 0 ? w - 1 : 0); ww <= (w + 1 < nw ? w + 1 : nw - 1); ++ww)
-            for (int q = ww * 32; q < ww * 32 + 32 && q < npb; ++q) {
-              if (c.Vv[VIT_HW + q] > seg) seg = c.Vv[VIT_HW + q];
-              if (c.Vu[VIT_HW + q] > um) um = c.Vu[VIT_HW + q];
-              if (ww == w && c.Vu[VIT_HW + q] < umin) umin = c.Vu[VIT_HW + q];
-            }
+            for (int q = ww * 32; q < ww * 32 + 32 && q < npb; ++q) if (c.Vv[VIT_HW + q] > seg) seg = c.Vv[VIT_HW + q];
           c.vvmax = seg;
-          c.u_half = vit3_pick_half(um - umin, tb.gap1[w], tb.gap5[w]);
-          if (c.nu > VIT_LIST_MAX && j % 32 == 0) ++half_hist[c.u_half == 1 ? 0 : c.u_half == 5 ? 1 : 2];
         }
         vit3_step_bin(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lpv[j], lp_unv[t], &nv, &nu, &av, &au);
         Vv[(size_t)wp * VP + VIT_HW + j] = nv; Vu[(size_t)wp * VP + VIT_HW + j] = nu;
@@ -248,7 +242,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     }
     const int lp_ = (int)((T - 1) & 1);
     for (int j = 0; j < npb; ++j) { V[(size_t)lp_ * npb + j].x = Vv[(size_t)lp_ * VP + VIT_HW + j]; V[(size_t)lp_ * npb + j].y = Vu[(size_t)lp_ * VP + VIT_HW + j]; }
-    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps; unvoiced scans by half-width 1/5/25: %ld %ld %ld\n", listed, skipped, half_hist[0], half_hist[1], half_hist[2]);
+    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps\n", listed, skipped);
   } else {
   for (int64_t t = 1; t < T; ++t) {
     const cf64* Vc = V.data() + (size_t)((t - 1) & 1) * npb;
