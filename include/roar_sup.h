@@ -71,7 +71,9 @@ typedef struct roar_sup_config {
   double  preemph;
   double  pad_value;        /* roar_fbank_forward: fill beyond seq_len */
   int32_t pad_to;           /* roar_fbank_forward: T padded to a multiple (0 = off) */
-  int32_t reserved0;
+  int32_t energy_mode;      /* 0: L2 norm of the linear spectrum (TTSDataset, dataset.py:751-753);
+                               1: L2 norm of the output features over the mel axis (EnergyFeaturizer,
+                               tts/parts/preprocessing/features.py:283-302) */
   /* pYIN (librosa.pyin keyword arguments as called at dataset.py:696-703) */
   double  pitch_fmin;
   double  pitch_fmax;

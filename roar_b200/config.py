@@ -29,7 +29,7 @@ class RoarSupConfig(ctypes.Structure):
         ("log_mode", ctypes.c_int32), ("exact_pad", ctypes.c_int32), ("log_guard", ctypes.c_double),
         ("has_preemph", ctypes.c_int32), ("normalize", ctypes.c_int32),
         ("preemph", ctypes.c_double), ("pad_value", ctypes.c_double),
-        ("pad_to", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("pad_to", ctypes.c_int32), ("energy_mode", ctypes.c_int32),
         ("pitch_fmin", ctypes.c_double), ("pitch_fmax", ctypes.c_double),
         ("pyin_frame_length", ctypes.c_int32), ("pyin_win_length", ctypes.c_int32),
         ("pyin_hop_length", ctypes.c_int32), ("n_thresholds", ctypes.c_int32),
@@ -61,6 +61,7 @@ class SupConfig:
     normalize: Optional[str] = None
     pad_value: float = 0.0
     pad_to: int = 0
+    energy_mode: str = "spectrum"        # "spectrum": TTSDataset energy; "features": EnergyFeaturizer (norm over mel axis)
     pitch_fmin: float = PITCH_FMIN_C2
     pitch_fmax: float = PITCH_FMAX_C7
     pyin_frame_length: Optional[int] = None   # None -> win_length (what TTSDataset passes)
@@ -117,6 +118,9 @@ class SupConfig:
         c.normalize = NORMALIZE[self.normalize]
         c.pad_value = float(self.pad_value)
         c.pad_to = int(self.pad_to)
+        if self.energy_mode not in ("spectrum", "features"):
+            raise ValueError(f"unsupported energy_mode {self.energy_mode!r}")
+        c.energy_mode = 1 if self.energy_mode == "features" else 0
         c.pitch_fmin = float(self.pitch_fmin)
         c.pitch_fmax = float(self.pitch_fmax)
         c.pyin_frame_length = int(self.pyin_frame)

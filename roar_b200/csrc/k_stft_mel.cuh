@@ -39,7 +39,7 @@ struct StftParams {
   int32_t P, G;               // threads per frame, frames in flight
   // options
   float floor_, mag_power, log_guard, preemph;
-  int32_t log_mode, has_preemph, use_tma, preemph_after_pad;
+  int32_t log_mode, has_preemph, use_tma, preemph_after_pad, energy_mode;
   // tables (device memory)
   const float* window;        // [n_fft]
   const cf32* tw;             // per-pass Stockham twiddles (fft.cuh layout), read through L1
@@ -260,7 +260,15 @@ HD void stft_phase_store(const StftParams& p, const StftTile& t, StftSmem& s, in
     }
   }
   if (p.energy) {
-    for (int f = tid; f < t.nf; f += nthr) p.energy[p.frame_off[t.utt] + t.t0 + f] = s.en[f];
+    for (int f = tid; f < t.nf; f += nthr) {
+      float e = s.en[f];
+      if (p.energy_mode == 1) {   // EnergyFeaturizer: torch.linalg.norm(features, axis=0)
+        float acc = 0.f;
+        for (int m = 0; m < p.n_mels; ++m) { const float v = s.out[m * (p.FT + 1) + f]; acc += v * v; }
+        e = sqrtf(acc);
+      }
+      p.energy[p.frame_off[t.utt] + t.t0 + f] = e;
+    }
   }
 }
 

@@ -104,7 +104,7 @@ static StftParams stft_params_base(const roar_sup_handle* h) {
   p.floor_ = (float)h->cfg.spec_floor; p.mag_power = (float)h->cfg.mag_power;
   p.log_guard = (float)h->cfg.log_guard; p.preemph = (float)h->cfg.preemph;
   p.log_mode = h->cfg.log_mode; p.has_preemph = h->cfg.has_preemph; p.use_tma = h->use_tma;
-  p.preemph_after_pad = h->cfg.exact_pad;
+  p.preemph_after_pad = h->cfg.exact_pad; p.energy_mode = h->cfg.energy_mode;
   p.window = h->d_window; p.tw = h->d_tw; p.tw_post = h->d_tw_post;
   p.mel_start = h->d_mel_start; p.mel_count = h->d_mel_count; p.mel_offset = h->d_mel_offset;
   p.mel_w = h->d_mel_w; p.mel_nw = h->mel_nw;

@@ -41,7 +41,7 @@ int emu_logmel_energy(const roar_sup_config* cfg, const float* audio, int64_t L,
   p.pad_left = cfg->exact_pad ? (g.n_fft - g.hop) / 2 : g.n_fft / 2;
   p.floor_ = (float)cfg->spec_floor; p.mag_power = (float)cfg->mag_power; p.log_guard = (float)cfg->log_guard;
   p.preemph = (float)cfg->preemph; p.log_mode = cfg->log_mode; p.has_preemph = cfg->has_preemph;
-  p.preemph_after_pad = cfg->exact_pad;
+  p.preemph_after_pad = cfg->exact_pad; p.energy_mode = cfg->energy_mode;
   p.window = win.data(); p.tw = tw.data(); p.tw_post = twp.data();
   p.mel_start = mr.start.data(); p.mel_count = mr.count.data(); p.mel_offset = mr.offset.data();
   p.mel_w = mr.weights.data(); p.mel_nw = (int)mr.weights.size();

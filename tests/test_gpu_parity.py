@@ -407,3 +407,69 @@ def test_cli_cache_layout_and_stats(tmp_path, capsys):
     res2 = X.main(argv)
     assert all(os.path.getmtime(p) == t for p, t in mt.items())
     assert abs(res2["pitch_mean"] - res["pitch_mean"]) < 1e-9 and abs(res2["pitch_std"] - res["pitch_std"]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_featurizers_vs_oracle_and_cli(tmp_path, c1):
+    """Row N2: MelSpectrogramFeaturizer / EnergyFeaturizer / PitchFeaturizer
+    (tts/parts/preprocessing/features.py:166-469) and the compute_features.py layout."""
+    import json
+    from scipy.io import wavfile
+    from oracle import fbank as ofbank
+    from oracle import pyin as opyin
+    from roar_b200 import compute_features as cf
+    from roar_b200 import featurizers as F
+    man, wavs = c1
+    wavs = [w[:22050 * 3] for w in wavs[:6]]
+    mel = F.MelSpectrogramFeaturizer()
+    energy = F.EnergyFeaturizer(spec_featurizer=mel)
+    # win 2048 / hop 512 at 22.05 kHz: transition width 101 -> the any-geometry Viterbi kernel
+    pitch = F.PitchFeaturizer(voiced_prob_name="voiced_prob", win_length=2048, hop_length=512)
+    mels = mel.compute_batch(wavs)["mel_spec"]
+    ens = energy.compute_batch(wavs)["energy"]
+    pit = pitch.compute_batch(wavs)
+    orc = ofbank.FilterbankFeaturesOracle(sample_rate=22050, n_window_size=1024, n_window_stride=256, nfilt=80,
+                                          n_fft=1024, lowfreq=0, highfreq=8000, mag_power=1.0, normalize=None,
+                                          log_zero_guard_type="add", log_zero_guard_value=1.0, pad_to=1,
+                                          mel_norm=None, preemph=None)
+    for i, w in enumerate(wavs):
+        ref, _ = orc.forward(w[None, :], [len(w)])
+        ref = np.asarray(ref[0])
+        got = mels[i].cpu().numpy()
+        assert got.shape == ref.shape
+        assert (np.abs(got - ref) / np.maximum(1, np.abs(ref))).max() <= 1e-4
+        ref_en = torch.linalg.norm(torch.from_numpy(ref), axis=0).numpy()
+        np.testing.assert_allclose(ens[i].cpu().numpy(), ref_en, rtol=1e-4)
+        of0, ovf, ovp = opyin.pyin(w, FMIN, FMAX, sr=22050, frame_length=2048, hop_length=512, fill_na=0.0)
+        assert pit["voiced_mask"][i].dtype == torch.bool and len(of0) == pit["pitch"][i].numel()
+        flags_ok, cents, dvp = _pyin_compare(pit["pitch"][i].cpu().numpy(),
+                                             pit["voiced_mask"][i].float().cpu().numpy(),
+                                             pit["voiced_prob"][i].cpu().numpy(), of0, ovf, ovp)
+        assert flags_ok.mean() >= 0.999 and (cents <= 1.0).mean() >= 0.999 and np.quantile(dvp, 0.999) <= 1e-4
+    # explicit hop != frame/4 (four autocorrelation blocks per frame)
+    p4 = F.PitchFeaturizer(voiced_prob_name="voiced_prob", win_length=2048, hop_length=256)
+    out4 = p4.compute_batch(wavs[:2])
+    for i, w in enumerate(wavs[:2]):
+        of0, ovf, ovp = opyin.pyin(w, FMIN, FMAX, sr=22050, frame_length=2048, hop_length=256, fill_na=0.0)
+        flags_ok, cents, dvp = _pyin_compare(out4["pitch"][i].cpu().numpy(), out4["voiced_mask"][i].float().cpu().numpy(),
+                                             out4["voiced_prob"][i].cpu().numpy(), of0, ovf, ovp)
+        assert flags_ok.mean() >= 0.999 and (cents <= 1.0).mean() >= 0.999
+    # CLI: same file layout as compute_features.py
+    audio_dir, feature_dir = tmp_path / "audio", tmp_path / "features"
+    (audio_dir / "spk0").mkdir(parents=True)
+    entries = []
+    for i, w in enumerate(wavs[:3]):
+        path = audio_dir / "spk0" / f"utt{i}.wav"
+        wavfile.write(path, 22050, w)
+        entries.append({"audio_filepath": f"spk0/utt{i}.wav", "text": "x"})
+    manifest = tmp_path / "manifest.json"
+    manifest.write_text("\n".join(json.dumps(e) for e in entries) + "\n")
+    cf.main([f"--manifest_path={manifest}", f"--audio_dir={audio_dir}", f"--feature_dir={feature_dir}"])
+    for i in range(3):
+        m = torch.load(feature_dir / "mel_spec" / "spk0" / f"utt{i}.pt")
+        assert m.shape == mels[i].shape and m.dtype == torch.float32 and not m.is_cuda
+        assert torch.allclose(m, mels[i].cpu(), rtol=1e-5, atol=1e-6)
+        assert torch.load(feature_dir / "voiced_mask" / "spk0" / f"utt{i}.pt").dtype == torch.bool
+        assert torch.load(feature_dir / "energy" / "spk0" / f"utt{i}.pt").shape == (m.shape[1],)
+    loaded = energy.load(entries[0], audio_dir, feature_dir)
+    assert set(loaded) == {"energy"}

@@ -150,3 +150,46 @@ def test_wav_decode_int16_and_float(tmp_path):
     assert a.dtype == np.float32 and np.array_equal(a, x) and np.abs(b - x).max() < 1e-4
     with pytest.raises(ValueError):
         X.load_wav(str(tmp_path / "f.wav"), 16000)
+
+
+def test_featurizer_paths_config_and_collate(tmp_path):
+    """Newer featurizer layout (tts/parts/preprocessing/features.py:84-160): file naming, YAML with
+    ``_target_`` / ``${...}`` in the reference's shape, padded collate."""
+    import torch
+    import yaml
+    from roar_b200 import compute_features as cf
+    from roar_b200 import featurizers as F
+    audio_dir, feature_dir = tmp_path / "audio", tmp_path / "feat"
+    e_rel = {"audio_filepath": "speaker1/audio1.wav"}
+    e_abs = {"audio_filepath": str(audio_dir / "speaker2" / "a.flac")}
+    assert F.get_feature_filepath(e_rel, audio_dir, feature_dir, "pitch") == feature_dir / "pitch" / "speaker1" / "audio1.pt"
+    assert F.get_feature_filepath(e_abs, audio_dir, feature_dir, "mel") == feature_dir / "mel" / "speaker2" / "a.pt"
+    cfg = {
+        "sample_rate": 22050, "win_length": 1024, "hop_length": 256,
+        "mel_feature": {"_target_": "roar.collections.tts.parts.preprocessing.features.MelSpectrogramFeaturizer",
+                        "sample_rate": "${sample_rate}", "win_length": "${win_length}", "hop_length": "${hop_length}",
+                        "mel_dim": 80, "lowfreq": 0, "highfreq": None},
+        "pitch_feature": {"_target_": "roar.collections.tts.parts.preprocessing.features.PitchFeaturizer",
+                          "sample_rate": "${sample_rate}", "win_length": "${win_length}", "hop_length": "${hop_length}",
+                          "pitch_fmin": 60, "pitch_fmax": 640},
+        "energy_feature": {"_target_": "roar.collections.tts.parts.preprocessing.features.EnergyFeaturizer",
+                           "spec_featurizer": "${mel_feature}"},
+        "featurizers": {"pitch": "${pitch_feature}", "energy": "${energy_feature}"},
+    }
+    p = tmp_path / "feature.yaml"
+    p.write_text(yaml.safe_dump(cfg, sort_keys=False))
+    fz = cf.load_featurizers(p)
+    assert list(fz) == ["pitch", "energy"]
+    assert isinstance(fz["pitch"], F.PitchFeaturizer) and fz["pitch"].cfg.pitch_fmax == 640.0
+    assert fz["pitch"].cfg.pyin_hop_length == 256 and fz["pitch"].voiced_prob_name is None
+    assert isinstance(fz["energy"].spec_featurizer, F.MelSpectrogramFeaturizer)
+    mel_cfg = fz["energy"].spec_featurizer.cfg
+    assert (mel_cfg.log_mode, mel_cfg.log_guard, mel_cfg.mel_norm, mel_cfg.spec_floor, mel_cfg.energy_mode) == \
+        ("add", 1.0, None, 0.0, "features")
+    with pytest.raises(ValueError):
+        cf._resolve({"featurizers": {"x": {"_target_": "a.b.UnknownFeaturizer"}}})
+    batch = [{"pitch": torch.ones(5), "voiced_mask": torch.ones(5, dtype=torch.bool)},
+             {"pitch": torch.ones(3), "voiced_mask": torch.zeros(3, dtype=torch.bool)}]
+    out = fz["pitch"].collate_fn(batch)
+    assert out["pitch"].shape == (2, 5) and out["pitch"][1, 3:].sum() == 0 and out["voiced_mask"].dtype == torch.bool
+    assert [len(b) for b in cf.make_batches([10, 50, 30, 20], 60)] == [1, 3]

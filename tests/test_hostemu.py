@@ -125,3 +125,21 @@ def test_emu_prior(golden_dir):
         assert np.abs(got - g[k]).max() < 2e-3
     got = hostemu.prior(50, 300, 0.5)
     assert np.abs(got - oprior.prior_f64(50, 300, 0.5)).max() < 1e-6
+
+
+def test_emu_featurizer_mel_and_energy():
+    """MelSpectrogramFeaturizer / EnergyFeaturizer arithmetic (features.py:166-302): magnitude mel,
+    log(x + 1), mel_norm=None, energy = L2 norm of the log-mel over the mel axis."""
+    import torch
+    y = _wav(2, 20000)
+    cfg = SupConfig(highfreq=8000.0, mel_norm=None, spec_floor=0.0, log_mode="add", log_guard=1.0, energy_mode="features")
+    lm, en = hostemu.logmel_energy(cfg, y)
+    ref, _ = ofbank.FilterbankFeaturesOracle(sample_rate=22050, n_window_size=1024, n_window_stride=256, nfilt=80,
+                                             n_fft=1024, lowfreq=0, highfreq=8000, mag_power=1.0, normalize=None,
+                                             log_zero_guard_type="add", log_zero_guard_value=1.0, pad_to=1,
+                                             mel_norm=None, preemph=None).forward(y[None, :], [len(y)])
+    ref = np.asarray(ref[0])
+    assert lm.shape == ref.shape
+    assert (np.abs(lm - ref) / np.maximum(1, np.abs(ref))).max() <= 1e-4
+    ref_en = torch.linalg.norm(torch.from_numpy(ref), axis=0).numpy()
+    np.testing.assert_allclose(en, ref_en, rtol=1e-4)
