@@ -103,14 +103,27 @@ HD FftPlan make_plan(int M) {
   return p;
 }
 
+// tw_total of make_plan(M) without materialising the plan
+HD int fft_tw_total(int M) {
+  int lg = 0;
+  while ((1 << lg) < M) ++lg;
+  int ns = 1, off = 0, first = 1;
+  while (lg > 0) {
+    const int r = lg >= 3 ? 8 : (lg == 2 ? 4 : 2);
+    if (!first) off += (r - 1) * ns;
+    first = 0; ns *= r; lg -= lg >= 3 ? 3 : lg;
+  }
+  return off;
+}
+
 // twiddle (from the pass table `twp`, forward sign; conjugated for the inverse) + butterfly
-template <int R, bool INV, class C>
+template <int R, bool INV, class C, bool RO = true>
 HD void stockham_twiddle_dft(C* v, int Ns, int j, const C* twp) {
   if (Ns > 1) {
     const int k = j & (Ns - 1);
 #pragma unroll
     for (int r = 1; r < R; ++r) {
-      C w = ld_ro(twp + (r - 1) * Ns + k);
+      C w = RO ? ld_ro(twp + (r - 1) * Ns + k) : twp[(r - 1) * Ns + k];   // RO: global table through L1
       if (INV) w.y = -w.y;
       v[r] = cmul(v[r], w);
     }

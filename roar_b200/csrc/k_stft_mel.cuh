@@ -55,6 +55,7 @@ struct StftParams {
 struct StftSmem {
   float* audio;     // [span]
   float* window;    // [n_fft]
+  cf32* tw;         // [tw_total] per-pass Stockham twiddles
   cf32* bufA;       // [G*MP]  MP = pidx(M): padded slot stride
   cf32* bufB;       // [G*MP]  (spec[G][n_bins] float aliases the buffer not holding the FFT result)
   float* part;      // [blockDim] energy partials
@@ -73,6 +74,7 @@ HD size_t stft_smem_carve(const StftParams& p, int nthreads, unsigned char* base
   CARVE(mbar, unsigned long long, 2)
   CARVE(audio, float, p.span)
   CARVE(window, float, p.n_fft)
+  CARVE(tw, cf32, fft_tw_total(p.M) + 1)
   CARVE(bufA, cf32, (size_t)p.G * pidx(p.M) + 8)
   CARVE(bufB, cf32, (size_t)p.G * pidx(p.M) + 8)
   CARVE(part, float, nthreads)
@@ -140,6 +142,10 @@ HD float stft_sample(const StftParams& p, const StftTile& t, int64_t pos) {
 // ---- phase A: tables + audio tile (generic path; the TMA path replaces the audio part on device)
 HD void stft_phase_tables(const StftParams& p, StftSmem& s, int tid, int nthr) {
   for (int i = tid; i < p.n_fft; i += nthr) s.window[i] = p.window[i];
+  {
+    const int nt = fft_tw_total(p.M);
+    for (int i = tid; i < nt; i += nthr) s.tw[i] = p.tw[i];
+  }
   for (int i = tid; i < p.n_mels; i += nthr) {
     s.mel_start[i] = p.mel_start[i]; s.mel_count[i] = p.mel_count[i]; s.mel_offset[i] = p.mel_offset[i];
   }
@@ -186,7 +192,7 @@ HD void stft_pass(const StftParams& p, const StftTile& t, StftSmem& s, int g, in
   for (int j = u; j < nb; j += p.P) {
     cf32 v[R];
     stockham_load<R>(v, in, p.M, j);
-    stockham_twiddle_dft<R, false>(v, Ns, j, twp);
+    stockham_twiddle_dft<R, false, cf32, false>(v, Ns, j, twp);   // twiddles staged in shared memory
     stockham_store<R>(v, out, Ns, j);
   }
 }
@@ -283,6 +289,9 @@ HD void stft_pass_any(int R, const StftParams& p, const StftTile& t, StftSmem& s
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// LG = log2(M): the radix plan (8,...,8[,4|2]) is a compile-time constant, so the pass loop unrolls and
+// nothing about the plan lives in local memory.
+template <int LG>
 __global__ void __launch_bounds__(256) k_stft_mel(const StftParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StftSmem s;
@@ -342,14 +351,21 @@ __global__ void __launch_bounds__(256) k_stft_mel(const StftParams p) {
   for (int g = 0; g < n_groups; ++g) {
     stft_first_pass<8>(p, t, s, g, tid);
     __syncthreads();
-    const FftPlan plan = make_plan(p.M);
-    int Ns = plan.radix[0];
+    constexpr int NP8 = LG / 3, REM = LG % 3;
+    int Ns = 8, off = 0;
     const cf32* src = s.bufA;
     cf32* dst = s.bufB;
-    for (int ps = 1; ps < plan.n_pass; ++ps) {
-      stft_pass_any(plan.radix[ps], p, t, s, g, tid, Ns, p.tw + plan.tw_off[ps], src, dst);
+#pragma unroll
+    for (int ps = 1; ps < NP8; ++ps) {
+      stft_pass<8>(p, t, s, g, tid, Ns, s.tw + off, src, dst);
       __syncthreads();
-      Ns *= plan.radix[ps];
+      off += 7 * Ns; Ns *= 8;
+      const cf32* tmp = src; src = dst; dst = const_cast<cf32*>(tmp);
+    }
+    if (REM != 0) {
+      if (REM == 2) stft_pass<4>(p, t, s, g, tid, Ns, s.tw + off, src, dst);
+      else stft_pass<2>(p, t, s, g, tid, Ns, s.tw + off, src, dst);
+      __syncthreads();
       const cf32* tmp = src; src = dst; dst = const_cast<cf32*>(tmp);
     }
     const cf32* zfin = src;            // FFT result

@@ -94,6 +94,7 @@ template <class T> static int upload(roar_sup_handle* h, const std::vector<T>& v
   return 0;
 }
 
+static void launch_stft(const roar_sup_handle* h, unsigned grid, cudaStream_t st, const StftParams& p);
 static StftParams stft_params_base(const roar_sup_handle* h) {
   StftParams p;
   memset(&p, 0, sizeof(p));
@@ -123,6 +124,18 @@ static PyinParams pyin_params_base(const roar_sup_handle* h) {
   p.thresholds = h->d_thr; p.beta_probs = h->d_beta; p.beta_cum = h->d_beta_cum;
   p.boltz_exp = h->d_bexp; p.boltz_fact = h->d_bfact;
   return p;
+}
+
+static void launch_stft(const roar_sup_handle* h, unsigned grid, cudaStream_t st, const StftParams& p) {
+  switch (p.M) {
+    case 32: k_stft_mel<5><<<grid, 256, h->stft_smem, st>>>(p); break;
+    case 64: k_stft_mel<6><<<grid, 256, h->stft_smem, st>>>(p); break;
+    case 128: k_stft_mel<7><<<grid, 256, h->stft_smem, st>>>(p); break;
+    case 256: k_stft_mel<8><<<grid, 256, h->stft_smem, st>>>(p); break;
+    case 512: k_stft_mel<9><<<grid, 256, h->stft_smem, st>>>(p); break;
+    case 1024: k_stft_mel<10><<<grid, 256, h->stft_smem, st>>>(p); break;
+    default: k_stft_mel<11><<<grid, 256, h->stft_smem, st>>>(p); break;
+  }
 }
 
 extern "C" {
@@ -220,7 +233,13 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     StftParams sp = stft_params_base(h);
     h->stft_smem = stft_smem_carve(sp, 256, nullptr, nullptr);
     if (h->stft_smem > h->max_smem) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "STFT tile does not fit in shared memory"); }
-    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
   }
   // ---- K2 / K3 tables
   {
@@ -396,7 +415,7 @@ int roar_sup_logmel_energy(roar_sup_handle* h, const float* d_audio, const int64
   p.tile_off = tile_off; p.n_utts = n_utts; p.logmel = d_logmel; p.energy = d_energy;
   LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, p.FT, tile_off));
   const int64_t max_tiles = total_frames / p.FT + n_utts;
-  LAUNCH(h, ROAR_K_STFT_MEL, st, k_stft_mel<<<(unsigned)max_tiles, 256, h->stft_smem, st>>>(p));
+  LAUNCH(h, ROAR_K_STFT_MEL, st, launch_stft(h, (unsigned)max_tiles, st, p));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -552,7 +571,7 @@ int roar_fbank_forward(roar_sup_handle* h, const float* d_x, const int64_t* d_le
   p.out_utt_stride = (int64_t)g.n_mels * Tpad; p.out_row_stride = Tpad;
   LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(frame_off, B, p.FT, tile_off));
   const int64_t max_tiles = (T_full * B) / p.FT + B;
-  LAUNCH(h, ROAR_K_STFT_MEL, st, k_stft_mel<<<(unsigned)max_tiles, 256, h->stft_smem, st>>>(p));
+  LAUNCH(h, ROAR_K_STFT_MEL, st, launch_stft(h, (unsigned)max_tiles, st, p));
   NormParams np;
   np.x = d_out; np.seq_len = d_out_len; np.B = B; np.n_mels = g.n_mels; np.T_full = (int32_t)T_full;
   np.Tpad = (int32_t)Tpad; np.mode = h->cfg.normalize; np.pad_value = (float)h->cfg.pad_value;
