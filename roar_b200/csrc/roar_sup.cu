@@ -405,8 +405,9 @@ int roar_sup_logmel_energy(roar_sup_handle* h, const float* d_audio, const int64
                            const int32_t* d_sample_len, int32_t n_utts, const int64_t* d_frame_off,
                            int64_t total_frames, float* d_logmel, float* d_energy, void* d_ws,
                            size_t ws_bytes, void* stream) {
-  if (!h || !d_audio || !d_sample_off || !d_sample_len || !d_frame_off) return fail(ROAR_ERR_INVALID_ARG, "null argument");
-  if (n_utts <= 0 || total_frames <= 0) return 0;
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
+  if (n_utts <= 0 || total_frames <= 0) return 0;   // empty batch: nothing to do (buffers may be null)
+  if (!d_audio || !d_sample_off || !d_sample_len || !d_frame_off) return fail(ROAR_ERR_INVALID_ARG, "null argument");
   if (ws_bytes < a256(sizeof(int32_t) * (size_t)(n_utts + 1)) || !d_ws) return fail(ROAR_ERR_WORKSPACE, "workspace too small for roar_sup_logmel_energy");
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* tile_off = (int32_t*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255);
@@ -424,9 +425,10 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
                   const int32_t* d_sample_len, int32_t n_utts, const int64_t* d_frame_off,
                   int64_t total_frames, int32_t max_T, float* d_f0, float* d_vflag, float* d_vprob,
                   void* d_ws, size_t ws_bytes, void* stream) {
-  if (!h || !d_audio || !d_sample_off || !d_sample_len || !d_frame_off || !d_f0 || !d_vflag || !d_vprob)
-    return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
   if (n_utts <= 0 || total_frames <= 0) return 0;
+  if (!d_audio || !d_sample_off || !d_sample_len || !d_frame_off || !d_f0 || !d_vflag || !d_vprob)
+    return fail(ROAR_ERR_INVALID_ARG, "null argument");
   if (max_T <= 0 || max_T > (1 << 20)) return fail(ROAR_ERR_INVALID_ARG, "max_frames_per_utt out of range");
   const Geometry& g = h->g;
   unsigned char* base = (unsigned char*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255);
@@ -481,8 +483,9 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
 int roar_sup_align_prior(roar_sup_handle* h, const int32_t* d_text_len, const int32_t* d_mel_len,
                          int32_t n_utts, const int64_t* d_out_off, int32_t max_mel_len,
                          double scaling_factor, float* d_prior, void* stream) {
-  if (!h || !d_text_len || !d_mel_len || !d_out_off || !d_prior) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
   if (n_utts <= 0 || max_mel_len <= 0) return 0;
+  if (!d_text_len || !d_mel_len || !d_out_off || !d_prior) return fail(ROAR_ERR_INVALID_ARG, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   PriorParams p;
   p.text_len = d_text_len; p.mel_len = d_mel_len; p.out_off = d_out_off; p.out = d_prior;
@@ -504,8 +507,9 @@ int roar_sup_pitch_partials_init(roar_sup_handle* h, double* d_out, int32_t n_gr
   return 0;
 }
 int roar_sup_pitch_partials(roar_sup_handle* h, const float* d_f0, int64_t n, double* d_out5, void* stream) {
-  if (!h || !d_f0 || !d_out5) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
   if (n <= 0) return 0;
+  if (!d_f0 || !d_out5) return fail(ROAR_ERR_INVALID_ARG, "null argument");
   int64_t nb = (n + 256 * 8 - 1) / (256 * 8);
   const int64_t cap = (int64_t)h->sm_count * 8;
   if (nb > cap) nb = cap;
@@ -516,8 +520,9 @@ int roar_sup_pitch_partials(roar_sup_handle* h, const float* d_f0, int64_t n, do
 int roar_sup_pitch_partials_grouped(roar_sup_handle* h, const float* d_f0, const int64_t* d_frame_off,
                                     const int32_t* d_group, int32_t n_utts, int32_t n_groups, double* d_out,
                                     void* stream) {
-  if (!h || !d_f0 || !d_frame_off || !d_group || !d_out) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
   if (n_utts <= 0) return 0;
+  if (!d_f0 || !d_frame_off || !d_group || !d_out) return fail(ROAR_ERR_INVALID_ARG, "null argument");
   const int64_t threads = (int64_t)n_utts * 32;
   k_pitch_partials_grouped<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       d_f0, d_frame_off, d_group, n_utts, n_groups, d_out);

@@ -145,6 +145,9 @@ class SupDataExtractor:
     def log_mel_energy(self, batch: PackedBatch, want_log_mel: bool = True, want_energy: bool = True):
         """-> (log_mel flat float32 [n_mels * sum T] or None, energy [sum T] or None, frame_off host int64).
         Utterance i's log-mel is ``log_mel[n_mels*fo[i] : n_mels*fo[i+1]].view(n_mels, T_i)``."""
+        if batch.n_utts == 0:   # empty manifest shard: nothing to launch
+            e = torch.empty(0, dtype=torch.float32, device=self.device)
+            return (e if want_log_mel else None), (e.clone() if want_energy else None), np.zeros(1, dtype=np.int64)
         self._check_lengths(batch, "log_mel_energy")
         T = self.num_frames(batch.lens_host)
         d_fo, fo = self._frame_off(T)
@@ -160,6 +163,9 @@ class SupDataExtractor:
 
     def pyin(self, batch: PackedBatch):
         """-> (f0, voiced_flag, voiced_prob) flat float32 [sum T], frame_off host int64."""
+        if batch.n_utts == 0:
+            e = torch.empty(0, dtype=torch.float32, device=self.device)
+            return e, e.clone(), e.clone(), np.zeros(1, dtype=np.int64)
         T = self.pyin_num_frames(batch.lens_host)
         d_fo, fo = self._frame_off(T)
         total = int(fo[-1])
@@ -170,7 +176,8 @@ class SupDataExtractor:
         _lib.check(self.lib.roar_sup_pyin(
             self._h, _ptr(batch.audio), _ptr(batch.sample_off), _ptr(batch.sample_len), batch.n_utts,
             _ptr(d_fo), total, int(T.max()), _ptr(f0), _ptr(vf), _ptr(vp), _ptr(ws), ws.numel(), self._stream()))
-        self.kernel_launches += 8
+        # 2 x tile offsets, energy, cmnd, probs, 3 x length sort, viterbi, backtrack
+        self.kernel_launches += 10
         return f0, vf, vp, fo
 
     def align_prior(self, text_lens, mel_lens, scaling_factor: float = 1.0):

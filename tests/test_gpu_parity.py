@@ -205,6 +205,17 @@ def test_pyin_44k_config4_vs_oracle():
         assert flags_ok.mean() >= 0.999 and (cents <= 1.0).mean() >= 0.999 and np.quantile(dvp, 0.999) <= 1e-4
 
 
+def test_empty_batch_and_too_short_input(ex):
+    """Edge cases: an empty shard is a no-op; audio not longer than the reflect pad is rejected like
+    torch.stft does in the reference (dataset.py:324-333)."""
+    out = ex.extract(ex.pack([]), text_lens=[])
+    assert out["log_mel"].numel() == 0 and out["pitch"].numel() == 0 and out["align_prior_matrix"].numel() == 0
+    with pytest.raises(ValueError):
+        ex.log_mel_energy(ex.pack([np.zeros(512, np.float32)]))
+    f0, vf, vp, fo = ex.pyin(ex.pack([np.zeros(512, np.float32)]))      # pYIN zero-pads: fine
+    assert f0.numel() == 3 and float(f0.abs().sum()) == 0.0
+
+
 def test_prior_vs_reference_golden(ex, golden_dir):
     """Against the reference's own outputs.  The reference evaluates the formula with float32 gammaln
     (its values are off the exact ones by up to ~2e-3 relative, measured below per case), so on rows
