@@ -161,6 +161,15 @@ int roar_sup_align_prior(roar_sup_handle* h, const int32_t* d_text_len, const in
                          int32_t n_utts, const int64_t* d_out_off, int32_t max_mel_len,
                          double scaling_factor, float* d_prior, void* stream);
 
+/* Interpolated prior: replaces BetaBinomialInterpolator.__call__(mel_len, text_len)
+ * (tts_dataset_utils.py:69-92; used when `use_beta_binomial_interpolator: true`): exact prior at sizes
+ * rounded to multiples of (round_mel_len_to, round_text_len_to) = (50, 10) by default, resampled to
+ * [mel_len, text_len] with scipy.ndimage.zoom(order=1) semantics.  Same output layout as above. */
+int roar_sup_align_prior_interp(roar_sup_handle* h, const int32_t* d_text_len, const int32_t* d_mel_len,
+                                int32_t n_utts, const int64_t* d_out_off, int32_t max_mel_len,
+                                int32_t round_mel_len_to, int32_t round_text_len_to, float* d_prior,
+                                void* stream);
+
 /* Partial pitch statistics over f0 != 0: replaces get_pitch_stats
  * (scripts/dataset_processing/tts/extract_sup_data.py:8-13, 29-30).
  *   d_out (float64) [n_groups, 5]: sum, sum of squares, count, min, max.  `_init` sets

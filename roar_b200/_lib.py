@@ -14,7 +14,7 @@ SYMBOLS = [
     "roar_sup_destroy", "roar_sup_num_frames", "roar_sup_pyin_num_frames", "roar_sup_pyin_geometry",
     "roar_sup_host_mel_filterbank", "roar_sup_host_window", "roar_sup_host_pyin_log_transition",
     "roar_sup_host_pyin_beta_probs", "roar_sup_workspace_bytes", "roar_sup_logmel_energy",
-    "roar_sup_pyin", "roar_sup_align_prior", "roar_sup_pitch_partials_init", "roar_sup_pitch_partials",
+    "roar_sup_pyin", "roar_sup_align_prior", "roar_sup_align_prior_interp", "roar_sup_pitch_partials_init", "roar_sup_pitch_partials",
     "roar_sup_pitch_partials_grouped", "roar_fbank_out_frames", "roar_fbank_forward",
     "roar_sup_set_profiling", "roar_sup_profile_read",
 ]
@@ -58,6 +58,7 @@ def load():
     lib.roar_sup_logmel_energy.argtypes = [vp, vp, vp, vp, i32, vp, i64, vp, vp, vp, ctypes.c_size_t, vp]
     lib.roar_sup_pyin.argtypes = [vp, vp, vp, vp, i32, vp, i64, i32, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.roar_sup_align_prior.argtypes = [vp, vp, vp, i32, vp, i32, f64, vp, vp]
+    lib.roar_sup_align_prior_interp.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, vp]
     lib.roar_sup_pitch_partials_init.argtypes = [vp, vp, i32, vp]
     lib.roar_sup_pitch_partials.argtypes = [vp, vp, i64, vp, vp]
     lib.roar_sup_pitch_partials_grouped.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]

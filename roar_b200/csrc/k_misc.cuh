@@ -41,7 +41,53 @@ HD float prior_value_real(const PriorParams& p, int N, int M, int y, int k) {
   return (float)exp(lc + lb1 - lb2);
 }
 
+// BetaBinomialInterpolator.__call__(w = mel_len, h = text_len) (tts_dataset_utils.py:69-92): the exact prior at
+// sizes rounded to multiples of (round_mel, round_text) -- with the reference's swapped roles,
+// bank(bw, bh) = prior(phoneme_count = bw, mel_count = bh), transposed -- resampled to [w, h] by
+// scipy.ndimage.zoom(order=1): output index o reads input coordinate o * (in - 1) / (out - 1), linear.
+// The LRU bank of the reference is a CPU cache; here the four taps are evaluated on the fly.
+HD int prior_round(int val, int to) {
+  // max(1, int(np.round((val + 1) / to))) * to ; np.round = round half to even
+  const double q = (double)(val + 1) / (double)to;
+  const int r = (int)rint(q);
+  return (r < 1 ? 1 : r) * to;
+}
+HD float prior_interp_value(const PriorParams& p, int w, int h, int bw, int bh, int i, int j) {
+  // scipy's NI_ZoomShift arithmetic, reproduced literally: zoom = (in - 1) / (out - 1) as one double
+  // division, coordinate = zoom * index; mode="constant" turns a coordinate that rounding pushed past
+  // in - 1 into cval = 0 (the reference inherits this: e.g. the last row of a 75 x 15 prior is zero).
+  const double zx = w > 1 ? (double)(bw - 1) / (double)(w - 1) : 1.0;
+  const double zy = h > 1 ? (double)(bh - 1) / (double)(h - 1) : 1.0;
+  const double x = zx * (double)i, y = zy * (double)j;
+  if (x > (double)(bw - 1) || y > (double)(bh - 1)) return 0.f;
+  const int i0 = (int)floor(x), j0 = (int)floor(y);
+  const int i1 = i0 + 1 < bw ? i0 + 1 : bw - 1, j1 = j0 + 1 < bh ? j0 + 1 : bh - 1;
+  const double fx = x - i0, fy = y - j0;
+  // base[i'][j'] = prior(N = bw, M = bh)[j'][i']  (mel index j', token index i')
+  const double b00 = prior_value_int(p, bw, bh, j0 + 1, i0), b01 = prior_value_int(p, bw, bh, j1 + 1, i0);
+  const double b10 = prior_value_int(p, bw, bh, j0 + 1, i1), b11 = prior_value_int(p, bw, bh, j1 + 1, i1);
+  const double a0 = b00 + (b01 - b00) * fy, a1 = b10 + (b11 - b10) * fy;
+  return (float)(a0 + (a1 - a0) * fx);
+}
+
 #ifdef __CUDACC__
+struct PriorInterpParams { PriorParams base; int32_t round_mel, round_text; };
+__global__ void __launch_bounds__(256) k_align_prior_interp(const PriorInterpParams q) {
+  const PriorParams& p = q.base;
+  const int utt = p.utt_base + blockIdx.y;
+  const int h = p.text_len[utt], w = p.mel_len[utt];
+  const int r0 = blockIdx.x * p.rows_per_cta;
+  if (r0 >= w || h <= 0) return;
+  const int r1 = r0 + p.rows_per_cta < w ? r0 + p.rows_per_cta : w;
+  const int bw = prior_round(w, q.round_mel), bh = prior_round(h, q.round_text);
+  float* out = p.out + p.out_off[utt];
+  const int64_t e0 = (int64_t)r0 * h, e1 = (int64_t)r1 * h;
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int i = (int)(e / h), j = (int)(e - (int64_t)i * h);
+    out[e] = prior_interp_value(p, w, h, bw, bh, i, j);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_align_prior(const PriorParams p) {
   const int utt = p.utt_base + blockIdx.y;
   const int N = p.text_len[utt], M = p.mel_len[utt];

@@ -500,6 +500,29 @@ int roar_sup_align_prior(roar_sup_handle* h, const int32_t* d_text_len, const in
   return 0;
 }
 
+int roar_sup_align_prior_interp(roar_sup_handle* h, const int32_t* d_text_len, const int32_t* d_mel_len,
+                                int32_t n_utts, const int64_t* d_out_off, int32_t max_mel_len,
+                                int32_t round_mel_len_to, int32_t round_text_len_to, float* d_prior,
+                                void* stream) {
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
+  if (n_utts <= 0 || max_mel_len <= 0) return 0;
+  if (!d_text_len || !d_mel_len || !d_out_off || !d_prior) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (round_mel_len_to < 1 || round_text_len_to < 1) return fail(ROAR_ERR_INVALID_ARG, "rounding steps must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  PriorInterpParams q;
+  q.base.text_len = d_text_len; q.base.mel_len = d_mel_len; q.base.out_off = d_out_off; q.base.out = d_prior;
+  q.base.lf = h->d_lf; q.base.lf_n = h->lf_n; q.base.rows_per_cta = 64; q.base.scaling = 1.0;
+  q.round_mel = round_mel_len_to; q.round_text = round_text_len_to;
+  const unsigned gx = (max_mel_len + q.base.rows_per_cta - 1) / q.base.rows_per_cta;
+  for (int32_t u0 = 0; u0 < n_utts; u0 += 65535) {
+    q.base.utt_base = u0;
+    const unsigned gy = n_utts - u0 < 65535 ? n_utts - u0 : 65535;
+    LAUNCH(h, ROAR_K_PRIOR, st, k_align_prior_interp<<<dim3(gx, gy), 256, 0, st>>>(q));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int roar_sup_pitch_partials_init(roar_sup_handle* h, double* d_out, int32_t n_groups, void* stream) {
   if (!h || !d_out || n_groups <= 0) return fail(ROAR_ERR_INVALID_ARG, "bad argument");
   k_stats_init<<<(n_groups + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_out, n_groups);

@@ -197,6 +197,23 @@ class SupDataExtractor:
         self.kernel_launches += (len(tl) + 65534) // 65535
         return out, oo
 
+    def align_prior_interp(self, text_lens, mel_lens, round_mel_len_to: int = 50, round_text_len_to: int = 10):
+        """``BetaBinomialInterpolator.__call__(mel_len, text_len)`` for a batch
+        (tts_dataset_utils.py:69-92): same return layout as :meth:`align_prior`."""
+        tl = np.asarray(text_lens, dtype=np.int32)
+        ml = np.asarray(mel_lens, dtype=np.int32)
+        oo = np.zeros(len(tl) + 1, dtype=np.int64)
+        np.cumsum(tl.astype(np.int64) * ml.astype(np.int64), out=oo[1:])
+        out = torch.empty(int(oo[-1]), dtype=torch.float32, device=self.device)
+        d_tl = torch.from_numpy(tl).to(self.device, non_blocking=True)
+        d_ml = torch.from_numpy(ml).to(self.device, non_blocking=True)
+        d_oo = torch.from_numpy(oo).to(self.device, non_blocking=True)
+        _lib.check(self.lib.roar_sup_align_prior_interp(self._h, _ptr(d_tl), _ptr(d_ml), len(tl), _ptr(d_oo),
+                                                        int(ml.max()) if len(ml) else 0, int(round_mel_len_to),
+                                                        int(round_text_len_to), _ptr(out), self._stream()))
+        self.kernel_launches += (len(tl) + 65534) // 65535
+        return out, oo
+
     def new_pitch_partials(self, n_groups: int = 1) -> torch.Tensor:
         out = torch.empty(n_groups, 5, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.roar_sup_pitch_partials_init(self._h, _ptr(out), n_groups, self._stream()))

@@ -64,3 +64,11 @@ def prior(N, M, scaling=1.0):
                          out.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0
     return out
+
+
+def prior_interp(text_len, mel_len, round_mel=50, round_text=10):
+    out = np.zeros((mel_len, text_len), np.float32)
+    rc = lib().emu_prior_interp(ctypes.c_int32(text_len), ctypes.c_int32(mel_len), ctypes.c_int32(round_mel),
+                                ctypes.c_int32(round_text), out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return out

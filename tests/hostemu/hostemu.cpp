@@ -281,4 +281,16 @@ int emu_prior(int32_t N, int32_t M, double scaling, float* out) {
   return 0;
 }
 
+int emu_prior_interp(int32_t text_len, int32_t mel_len, int32_t round_mel, int32_t round_text, float* out) {
+  std::vector<double> lf(8192);
+  for (size_t i = 0; i < lf.size(); ++i) lf[i] = std::lgamma((double)i + 1.0);
+  PriorParams p;
+  memset(&p, 0, sizeof(p));
+  p.lf = lf.data(); p.lf_n = (int)lf.size(); p.scaling = 1.0;
+  const int w = mel_len, h = text_len, bw = prior_round(w, round_mel), bh = prior_round(h, round_text);
+  for (int i = 0; i < w; ++i)
+    for (int j = 0; j < h; ++j) out[(size_t)i * h + j] = prior_interp_value(p, w, h, bw, bh, i, j);
+  return 0;
+}
+
 }  // extern "C"

@@ -267,6 +267,20 @@ def test_prior_vs_float64_and_scaling(ex):
     assert np.abs(got[ref > 1e-30] / ref[ref > 1e-30] - 1).max() < 1e-5
 
 
+def test_prior_interpolator_vs_oracle(ex):
+    """Row a9: BetaBinomialInterpolator through roar_sup_align_prior_interp."""
+    from oracle import prior as oprior
+    it = oprior.BetaBinomialInterpolator()
+    tl = [100, 15, 1, 2, 141, 47, 31]
+    ml = [560, 75, 1, 99, 812, 333, 149]
+    flat, oo = ex.align_prior_interp(tl, ml)
+    for i, (h, w) in enumerate(zip(tl, ml)):
+        got = flat[oo[i]:oo[i + 1]].view(w, h).cpu().numpy()
+        ref = it(w, h)
+        assert np.abs(got - ref).max() < 2e-4
+        assert np.array_equal((got == 0).all(axis=1), (ref == 0).all(axis=1))
+
+
 def test_pitch_stats(ex):
     from oracle import stats as ostats
     from roar_b200.extractor import finalize_pitch_stats

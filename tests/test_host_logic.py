@@ -193,3 +193,25 @@ def test_featurizer_paths_config_and_collate(tmp_path):
     out = fz["pitch"].collate_fn(batch)
     assert out["pitch"].shape == (2, 5) and out["pitch"][1, 3:].sum() == 0 and out["voiced_mask"].dtype == torch.bool
     assert [len(b) for b in cf.make_batches([10, 50, 30, 20], 60)] == [1, 3]
+
+
+def test_pitch_normalisation_and_stats_selection(tmp_path):
+    import json
+    import torch
+    from oracle import stats as ostats
+    from roar_b200 import dataset_utils as du
+    pitch = np.array([0.0, 110.0, 0.0, 220.5, 98.7], dtype=np.float32)
+    ref = ostats.normalize_pitch(pitch, 150.25, 42.5)
+    got = du.normalize_pitch(torch.from_numpy(pitch.copy()), 150.25, 42.5).numpy()
+    assert np.array_equal(got, ref) and got[0] == 0 and got[2] == 0
+    stats = {"default": {"pitch_mean": 100.0, "pitch_std": 10.0}, "7": {"pitch_mean": 200.0, "pitch_std": 20.0}}
+    p = tmp_path / "pitch_stats.json"
+    p.write_text(json.dumps(stats))
+    st = du.load_pitch_stats(p)
+    assert du.select_pitch_stats({"speaker_id": 7}, pitch_stats=st) == (200.0, 20.0)
+    assert du.select_pitch_stats({"speaker_id": 9}, pitch_stats=st) == (100.0, 10.0)
+    assert du.select_pitch_stats({"speaker_id": 7}, 1.0, 2.0, st) == (1.0, 2.0)
+    with pytest.raises(ValueError):
+        du.select_pitch_stats({}, pitch_stats={"3": stats["7"]})
+    with pytest.raises(ValueError):
+        du.select_pitch_stats({})

@@ -143,3 +143,20 @@ def test_emu_featurizer_mel_and_energy():
     assert (np.abs(lm - ref) / np.maximum(1, np.abs(ref))).max() <= 1e-4
     ref_en = torch.linalg.norm(torch.from_numpy(ref), axis=0).numpy()
     np.testing.assert_allclose(en, ref_en, rtol=1e-4)
+
+
+def test_emu_prior_interpolator():
+    """BetaBinomialInterpolator (tts_dataset_utils.py:69-92): rounded-size prior + ndimage.zoom(order=1),
+    including scipy's artefact of zeroing a last row/column whose coordinate rounds past the input."""
+    it = oprior.BetaBinomialInterpolator()
+    zero_cases = 0
+    for w, h in [(560, 100), (75, 15), (1, 1), (2, 1), (99, 2), (812, 141), (333, 47), (50, 10), (149, 31)]:
+        ref = it(w, h)
+        got = hostemu.prior_interp(h, w)
+        assert got.shape == ref.shape == (w, h)
+        assert np.abs(got - ref).max() < 2e-4
+        big = ref > 1e-30          # ignore float32-underflow noise of the reference's gammaln
+        assert np.array_equal(got[big] == 0, ref[big] == 0)
+        assert np.array_equal((got == 0).all(axis=1), (ref == 0).all(axis=1))
+        zero_cases += int((ref == 0).all(axis=1).any() or (ref == 0).all(axis=0).any())
+    assert zero_cases >= 1     # (75, 15) has the zeroed last row / column
