@@ -120,6 +120,8 @@ def main():
     ap.add_argument("--e2e-chunk-utts", type=int, default=1640, help="utterances per streamed host chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cache-write-utts", type=int, default=512,
+                    help="also time writing the .pt cache (5 files per utterance) for this many utterances; 0 = skip")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -309,6 +311,42 @@ def main():
                "ms_per_step": 1e3 * e2e_s / args.steps,
                "pitch_mean": finalize_pitch_stats(host_stats)["pitch_mean"]}
 
+    # ------------------------------------------------------------------ .pt cache writing
+    cache_write = None
+    if rank == 0 and args.cache_write_utts > 0:
+        import shutil
+        import tempfile
+        from pathlib import Path
+        from roar_b200.extract_sup_data import CacheWriter
+        nw = min(args.cache_write_utts, n_utts)
+        lo = int(offs_h[0]); hi = int(offs_h[nw - 1] + (lens_h[nw - 1] + 3) // 4 * 4)
+        bt = ex.batch_from_device(audio[lo:hi], offs_h[:nw] - lo, lens_h[:nw])
+        out = ex.extract(bt, text_lens=text_lens[:nw])
+        torch.cuda.synchronize()
+        tmp = Path(tempfile.mkdtemp(prefix="roar_sup_cache_"))
+        try:
+            names = ("log_mel", "pitch", "voiced_mask", "p_voiced", "energy")
+            for k in names:
+                (tmp / k).mkdir()
+            writer = CacheWriter(8)
+            t0 = time.perf_counter()
+            host = {k: out[k].cpu() for k in names}
+            fo = out["frame_off"]
+            for i in range(nw):
+                a, b = int(fo[i]), int(fo[i + 1])
+                for k in names:
+                    ten = host[k][N_MELS * a:N_MELS * b].view(1, N_MELS, b - a) if k == "log_mel" else host[k][a:b]
+                    writer.submit(ten.clone(), tmp / k / f"utt{i}.pt")
+            writer.drain()
+            dt = time.perf_counter() - t0
+            cache_write = {"utterances": nw, "files": 5 * nw, "seconds": dt, "files_per_s": 5 * nw / dt,
+                           "audio_s_per_s": float(lens_h[:nw].sum()) / SR / dt,
+                           "note": "D2H + torch.save of the five cached types through the CLI's writer pool "
+                                   "(8 threads, temp file + rename); outside the timed extraction region"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        del out
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -388,6 +426,8 @@ def main():
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if cache_write is not None:
+        line["cache_write"] = cache_write
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line))
