@@ -151,7 +151,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n = max(8, min(cores, 64))
+        n = max(8, min(4 * cores, 128))      # ~10-30 s of CPU work on the box's cores
         audio, wall, cores, per_step = cpu_reference_run(1, 0, n)
         cpu_baseline = {"value": audio / wall, "unit": "audio-s/s", "cores": cores, "kind": "port",
                         "sample": f"first {n} utterances ({audio:.0f} audio-s) of the config-2 manifest, oracle "
