@@ -404,6 +404,13 @@ def main():
                 "algorithmic_bytes_per_launch": dom_alg // n_launch, "ms_per_launch": dom_ms / n_launch,
                 "note": "FP64-pipe / latency bound, not HBM bound (DESIGN.md section 4); "
                         "frac is the honest HBM fraction of its algorithmic bytes"}
+    # every kernel of the path against the same HBM peak (algorithmic bytes of that kernel alone)
+    roofline_kernels = {}
+    for k, b in alg.items():
+        if per.get(k, 0) > 0:
+            gbs = b / (per[k] * 1e-3) / 1e9
+            roofline_kernels[k] = {"ms_per_step": round(per[k], 4), "algorithmic_bytes": int(b),
+                                   "achieved_gbs": round(gbs, 2), "frac": round(gbs / hbm_peak, 5)}
     path_bytes = 4 * samples + 4 * (N_MELS + 4) * frames + 4 * prior_elems
     step_ms = total_ms / args.steps
     value = world * audio_s * args.steps / (total_ms * 1e-3)
@@ -419,6 +426,7 @@ def main():
         "gpu_launches": launches, "clocks": clocks,
         "kernels_ms_per_step": {k: round(v, 4) for k, v in per.items() if v > 0},
         "roofline": roofline,
+        "roofline_kernels": roofline_kernels,
         "roofline_path": {"bound": "hbm", "achieved": path_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak,
                           "unit": "GB/s", "frac": path_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
                           "algorithmic_bytes_per_step": path_bytes},
