@@ -205,6 +205,8 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
   roar_sup_handle* h = new roar_sup_handle();
   h->cfg = *cfg; h->g = geometry(*cfg); h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  // The opt-in limit is a per-FUNCTION attribute shared by every handle in the process, so each kernel is
+  // opened up to the device maximum once; a launch still asks only for what its own geometry needs.
   h->max_smem = prop.sharedMemPerBlockOptin;
   const Geometry& g = h->g;
   if (g.pf < 256) { delete h; return fail(ROAR_ERR_UNSUPPORTED, "pyin_frame_length < 256 is not supported"); }
@@ -233,13 +235,13 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     StftParams sp = stft_params_base(h);
     h->stft_smem = stft_smem_carve(sp, 256, nullptr, nullptr);
     if (h->stft_smem > h->max_smem) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "STFT tile does not fit in shared memory"); }
-    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stft_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
   }
   // ---- K2 / K3 tables
   {
@@ -277,11 +279,11 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     h->cmnd_smem = cmnd_smem_carve(pp, nullptr, nullptr);
     h->prob_smem = prob_smem_carve(pp, nullptr, nullptr) * 8 + sizeof(double) * (2 * (g.n_thr + 2) + 2 * (g.kmax + 2));
     if (h->cmnd_smem > h->max_smem || h->prob_smem > h->max_smem) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "pYIN tile does not fit in shared memory"); }
-    CUDA_TRY(cudaFuncSetAttribute(k_pyin_cmnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cmnd_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_cmnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
     h->energy_smem = sizeof(float) * (size_t)(epad(energy_span(pp), g.ph) + 4);
     if (h->energy_smem > h->max_smem) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "pYIN energy tile does not fit in shared memory"); }
-    CUDA_TRY(cudaFuncSetAttribute(k_pyin_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->energy_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_pyin_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->prob_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
     h->vit_threads = (g.npb + 31) / 32 * 32;
     if (h->vit_threads < g.kmax) { roar_sup_destroy(h); return fail(ROAR_ERR_UNSUPPORTED, "kmax exceeds Viterbi block size"); }
     size_t base = sizeof(cf64) * 2 * g.npb + sizeof(double) * 2 * g.npb + sizeof(double) * 64 + sizeof(int) * 64 +
@@ -289,10 +291,10 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     size_t ltb = sizeof(double) * 2 * (size_t)t.n_rows * g.tw;
     h->lt_in_smem = base + ltb <= h->max_smem ? 1 : 0;
     h->vit_smem = base + (h->lt_in_smem ? ltb : 0);
-    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<true, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<false, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<true, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<false, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
     // fast path: the reference geometry (transition width 51), row ids in 6 bits
     h->vit3_smem = sizeof(Vit3Shared);
     // ROAR_SUP_VITERBI=generic forces the any-geometry kernel (tests compare the two)
@@ -300,7 +302,7 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     h->vit_fast = (g.tw == VIT_TW && t.n_rows + 1 <= VIT_ROWS_MAX && g.npb <= VIT_NPB_MAX && g.kmax <= VIT_KMAX_MAX &&
                    h->vit3_smem <= h->max_smem && !(env_v && env_v[0] == 'g')) ? 1 : 0;
     if (h->vit_fast)
-      CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi51, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->vit3_smem));
+      CUDA_TRY(cudaFuncSetAttribute(k_pyin_viterbi51, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
   }
   // ---- K4 log-factorial table
   {

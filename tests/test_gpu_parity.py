@@ -205,6 +205,20 @@ def test_pyin_44k_config4_vs_oracle():
         assert flags_ok.mean() >= 0.999 and (cents <= 1.0).mean() >= 0.999 and np.quantile(dvp, 0.999) <= 1e-4
 
 
+def test_handles_with_different_geometries_coexist(ex, c1):
+    """Kernel attributes are per function, not per handle: creating a handle with a smaller tile must not
+    break launches of an existing one (regression)."""
+    from roar_b200.config import SupConfig
+    from roar_b200.extractor import SupDataExtractor
+    man, wavs = c1
+    before = ex.pyin(ex.pack(wavs[:3]))
+    small = SupDataExtractor(SupConfig(sample_rate=16000, n_fft=256, hop_length=64, n_mels=40, pyin_frame_length=256))
+    small.extract(small.pack([w[:8000] for w in wavs[:2]]), text_lens=[5, 7])
+    after = ex.pyin(ex.pack(wavs[:3]))
+    lm = ex.log_mel_energy(ex.pack(wavs[:3]))
+    assert torch.equal(before[0], after[0]) and torch.isfinite(lm[0]).all()
+
+
 def test_empty_batch_and_too_short_input(ex):
     """Edge cases: an empty shard is a no-op; audio not longer than the reflect pad is rejected like
     torch.stft does in the reference (dataset.py:324-333)."""
@@ -265,6 +279,29 @@ def test_prior_vs_float64_and_scaling(ex):
     ref = oprior.prior_f64(50, 300, 0.5)
     got = out.view(300, 50).cpu().numpy()
     assert np.abs(got[ref > 1e-30] / ref[ref > 1e-30] - 1).max() < 1e-5
+
+
+@pytest.mark.parametrize("kw,okw", [
+    (dict(pyin_win_length=600), dict(win_length=600)),
+    (dict(pyin_hop_length=128), dict(hop_length=128)),
+    (dict(pyin_win_length=384, pyin_hop_length=128), dict(win_length=384, hop_length=128)),
+])
+def test_pyin_block_geometries_vs_oracle(c1, kw, okw):
+    """Autocorrelation block decomposition for window / hop combinations other than W = 2 * hop."""
+    from oracle import pyin as opyin
+    from roar_b200.config import SupConfig
+    from roar_b200.extractor import SupDataExtractor, split_frames
+    man, wavs = c1
+    wavs = [w[:22050 * 2] for w in wavs[:4]]
+    exg = SupDataExtractor(SupConfig(highfreq=8000.0, **kw))
+    f0, vf, vp, fo = exg.pyin(exg.pack(wavs))
+    f0s, vfs, vps = split_frames(f0, fo), split_frames(vf, fo), split_frames(vp, fo)
+    for i, w in enumerate(wavs):
+        of0, ovf, ovp = opyin.pyin(w, FMIN, FMAX, sr=22050, frame_length=1024, fill_na=0.0, **okw)
+        assert len(of0) == f0s[i].numel()
+        flags_ok, cents, dvp = _pyin_compare(f0s[i].cpu().numpy(), vfs[i].cpu().numpy(), vps[i].cpu().numpy(),
+                                             of0, ovf, ovp)
+        assert flags_ok.mean() >= 0.999 and (cents <= 1.0).mean() >= 0.999 and np.quantile(dvp, 0.999) <= 1e-4
 
 
 def test_prior_interpolator_vs_oracle(ex):

@@ -71,6 +71,15 @@ def test_emu_fbank_exact_pad_preemph_order():
     assert (np.abs(lm - ref[0]) / np.maximum(1, np.abs(ref[0]))).max() <= 1e-4
 
 
+def cm_lags(cfg):
+    """number of CMND lags of a configuration (librosa: min_period .. max_period)"""
+    frame = cfg.pyin_frame
+    win = cfg.pyin_win_length or frame // 2
+    min_period = int(np.floor(cfg.sample_rate / cfg.pitch_fmax))
+    max_period = min(int(np.ceil(cfg.sample_rate / cfg.pitch_fmin)), frame - win - 1)
+    return max_period - min_period + 1
+
+
 @pytest.mark.parametrize("i,n", [(0, 44100), (1, 30000), (2, 9000)])
 def test_emu_pyin_equals_oracle(i, n):
     cfg = SupConfig(highfreq=8000.0)
@@ -160,3 +169,19 @@ def test_emu_prior_interpolator():
         assert np.array_equal((got == 0).all(axis=1), (ref == 0).all(axis=1))
         zero_cases += int((ref == 0).all(axis=1).any() or (ref == 0).all(axis=0).any())
     assert zero_cases >= 1     # (75, 15) has the zeroed last row / column
+
+
+@pytest.mark.parametrize("kw,okw", [
+    (dict(pyin_win_length=600), dict(win_length=600)),                       # W not a multiple of hop: one block per frame
+    (dict(pyin_hop_length=128), dict(hop_length=128)),                       # W = 4 * hop: four shared blocks per frame
+    (dict(pyin_win_length=384, pyin_hop_length=128), dict(win_length=384, hop_length=128)),
+])
+def test_emu_pyin_block_geometries(kw, okw):
+    """The block decomposition of the autocorrelation for non-default window / hop combinations."""
+    cfg = SupConfig(highfreq=8000.0, **kw)
+    y = _wav(5, 16000)
+    f0, vf, vp, cm, st = hostemu.pyin(cfg, y, cm_lags(cfg))
+    of0, ovf, ovp, info = opyin.pyin(y, FMIN, FMAX, sr=22050, frame_length=1024, fill_na=0.0, return_internals=True, **okw)
+    assert cm.shape == info["yin_frames"].T.shape
+    assert np.abs(cm - info["yin_frames"].T).max() < 1e-9
+    assert np.array_equal(st, info["states"]) and np.abs(vp - ovp).max() < 1e-6
