@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
 // + 2 compare/select.
 constexpr int VIT_TW = 51;
 constexpr int VIT_HW = 25;
-constexpr int VIT_LIST_MAX = 64;
+constexpr int VIT_LIST_MAX = 32;
 constexpr int VIT_CHAINS = 1;
 constexpr int VIT_RID_REGS = (VIT_TW + 4) / 5;   // 11
 constexpr double VIT_NEG = -1e308;
