@@ -8,10 +8,15 @@ namespace roar {
 // ------------------------------------------------------------------------------------ K4 prior
 // Replaces beta_binomial_prior_distribution (tts/parts/utils/tts_dataset_utils.py:128-149):
 //   P[y-1, k] = exp( lnC(n,k) + lnB(k+a, n-k+b) - lnB(a,b) ),  n=N-1, a=s*y, b=s*(M+1-y), y=1..M, k=0..N-1
-// With the scaling factor s == 1 every gammaln argument is a positive integer, so the whole
-// expression is a sum of nine log-factorials LF[i] = ln(i!) looked up in a float64 table built once
-// per handle (L1/L2 resident); the reference's float32 gammaln noise (~1e-3 relative) is not
-// reproduced -- the float64 value is rounded once.  Output is write-bound: 4*M*N bytes.
+// The reference evaluates this in FLOAT32 (torch.special.gammaln on float32 tensors, float32 adds), and
+// its rounding noise (~1e-3 relative in P) decides the row arg-max near every mode crossover, so the
+// kernel reproduces that arithmetic instead of the exact value: with the scaling factor s == 1 every
+// gammaln argument is a positive integer, torch's float32 gammaln of an integer is the correctly rounded
+// float32 of ln((i-1)!) (checked for i < 5000 in tests/), taken here from a float64 log-factorial table
+// built once per handle, and the nine terms are combined with the reference's own association:
+//   logcomb = (G(n+1) - G(k+1)) - G(n-k+1);  logbeta(u, v) = (G(u) + G(v)) - G(u+v);
+//   s = (logcomb + logbeta(k+a, n-k+b)) - logbeta(a, b);   P = exp(s).
+// Output is write-bound: 4*M*N bytes.
 struct PriorParams {
   const int32_t* text_len;
   const int32_t* mel_len;
@@ -25,13 +30,32 @@ struct PriorParams {
 };
 
 HD double prior_lf(const PriorParams& p, int i) { return i < p.lf_n ? p.lf[i] : lgamma((double)i + 1.0); }
-
-HD float prior_value_int(const PriorParams& p, int N, int M, int y, int k) {
+// float32 gammaln(i) for integer i >= 1, correctly rounded
+HD float prior_g32(const PriorParams& p, int i) { return (float)prior_lf(p, i - 1); }
+HD float prior_add32(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b; return r;
+#endif
+}
+HD float prior_sub32(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  volatile float r = a - b; return r;
+#endif
+}
+// float32 log-probability exactly as the reference forms it (s == 1)
+HD float prior_logp32(const PriorParams& p, int N, int M, int y, int k) {
   const int n = N - 1;
-  const double lc = prior_lf(p, n) - prior_lf(p, k) - prior_lf(p, n - k);
-  const double lb1 = prior_lf(p, k + y - 1) + prior_lf(p, n - k + M - y) - prior_lf(p, n + M);
-  const double lb2 = prior_lf(p, y - 1) + prior_lf(p, M - y) - prior_lf(p, M);
-  return (float)exp(lc + lb1 - lb2);
+  const float lc = prior_sub32(prior_sub32(prior_g32(p, n + 1), prior_g32(p, k + 1)), prior_g32(p, n - k + 1));
+  const float lb1 = prior_sub32(prior_add32(prior_g32(p, k + y), prior_g32(p, n - k + M + 1 - y)), prior_g32(p, n + M + 1));
+  const float lb2 = prior_sub32(prior_add32(prior_g32(p, y), prior_g32(p, M + 1 - y)), prior_g32(p, M + 1));
+  return prior_sub32(prior_add32(lc, lb1), lb2);
+}
+HD float prior_value_int(const PriorParams& p, int N, int M, int y, int k) {
+  return (float)exp((double)prior_logp32(p, N, M, y, k));
 }
 HD float prior_value_real(const PriorParams& p, int N, int M, int y, int k) {
   const double n = N - 1, a = p.scaling * y, b = p.scaling * (M + 1 - y);

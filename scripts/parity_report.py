@@ -1,0 +1,95 @@
+"""Full BASELINE config-1 parity report: all 100 synthetic utterances (full length) through the CUDA path
+and through the CPU oracle (one process per core), measured against the north-star gates.
+Test infrastructure (uses oracle/).   usage: python scripts/parity_report.py [out.json] [n_utts]"""
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _oracle(args):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import extract as oextract
+    from roar_b200 import synth
+    seed, utt_id, n, sr, spk, tl = args
+    y = synth.synth_utterance(seed, utt_id, n, sr, spk)
+    return oextract.extract_utterance(y, tl, sr=sr, dense_viterbi=False)
+
+
+def main():
+    out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/parity_c1.json"
+    n_utts = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    import torch
+    from oracle import pyin as opyin
+    from oracle import stats as ostats
+    from roar_b200 import synth
+    from roar_b200.config import SupConfig
+    from roar_b200.extractor import SupDataExtractor, finalize_pitch_stats, split_frames
+    man = synth.corpus_manifest("C1", n_utts)
+    tasks = [(1234, u.utt_id, u.n_samples, 22050, u.speaker, u.text_len) for u in man]
+    opyin.pyin(np.zeros(4096, np.float32), 65.4, 2093.0, sr=22050, frame_length=1024, fill_na=0.0)   # numba warm-up
+    t0 = time.time()
+    with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+        refs = pool.map(_oracle, tasks, chunksize=1)
+    t_cpu = time.time() - t0
+    wavs = [synth.synth_utterance(*t[:5]) for t in tasks]
+    ex = SupDataExtractor(SupConfig(highfreq=8000.0))
+    stats = ex.new_pitch_partials(1)
+    out = ex.extract(ex.pack(wavs), text_lens=[u.text_len for u in man], stats=stats)
+    torch.cuda.synchronize()
+    fo, oo = out["frame_off"], out["prior_off"]
+    lms = split_frames(out["log_mel"], fo, 80)
+    frames = voiced = flag_ok = cent_ok = argmax_ok = 0
+    worst_lm = worst_en = worst_vp = 0.0
+    all_pitch = []
+    for i, r in enumerate(refs):
+        a, b = int(fo[i]), int(fo[i + 1])
+        lm = lms[i].cpu().numpy()
+        worst_lm = max(worst_lm, float((np.abs(lm - r["log_mel"][0]) / np.maximum(1, np.abs(r["log_mel"][0]))).max()))
+        en = out["energy"][a:b].cpu().numpy()
+        worst_en = max(worst_en, float((np.abs(en - r["energy"]) / np.maximum(1e-12, np.abs(r["energy"]))).max()))
+        f0 = out["pitch"][a:b].cpu().numpy()
+        vf = out["voiced_mask"][a:b].cpu().numpy()
+        vp = out["p_voiced"][a:b].cpu().numpy()
+        frames += b - a
+        flag_ok += int((vf == r["voiced_mask"]).sum())
+        both = (vf != 0) & (r["voiced_mask"] != 0)
+        cents = np.abs(1200 * np.log2(f0[both] / r["pitch"][both]))
+        voiced += int(both.sum())
+        cent_ok += int((cents <= 1.0).sum())
+        worst_vp = max(worst_vp, float(np.abs(vp - r["p_voiced"]).max()))
+        pr = out["align_prior_matrix"][oo[i]:oo[i + 1]].view(b - a, man[i].text_len).cpu().numpy()
+        argmax_ok += int((pr.argmax(1) == r["align_prior_matrix"].argmax(1)).sum())
+        all_pitch.append(r["pitch"])
+    got = finalize_pitch_stats(stats)
+    ref = ostats.pitch_stats_f64(all_pitch)
+    rep = {
+        "workload": f"C1: {n_utts} synthetic 22.05 kHz utterances, full length ({frames} frames)",
+        "log_mel_max_rel_err (|a-b|/max(1,|b|))": worst_lm, "energy_max_rel_err": worst_en,
+        "voiced_flag_exact_frac": flag_ok / frames, "f0_within_1_cent_frac_of_voiced": cent_ok / max(1, voiced),
+        "voiced_frames": voiced, "p_voiced_max_abs_err": worst_vp,
+        "prior_argmax_exact_frac": argmax_ok / frames,
+        "pitch_mean_rel_err": abs(got["pitch_mean"] - ref["mean"]) / ref["mean"],
+        "pitch_std_rel_err": abs(got["pitch_std"] - ref["std"]) / ref["std"],
+        "gates": {"log_mel/energy": 1e-4, "f0": ">= 0.999 within 1 cent", "flags/prior argmax": ">= 0.999 exact",
+                  "pitch stats": 1e-5},
+        "oracle_cpu_seconds": t_cpu, "cpu_cores": os.cpu_count(),
+    }
+    ok = (worst_lm <= 1e-4 and worst_en <= 1e-4 and rep["voiced_flag_exact_frac"] >= 0.999
+          and rep["f0_within_1_cent_frac_of_voiced"] >= 0.999 and rep["prior_argmax_exact_frac"] >= 0.999
+          and rep["pitch_mean_rel_err"] <= 1e-5 and rep["pitch_std_rel_err"] <= 1e-5)
+    rep["all_gates_pass"] = bool(ok)
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+    with open(out_path, "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -231,50 +231,41 @@ def test_empty_batch_and_too_short_input(ex):
 
 
 def test_prior_vs_reference_golden(ex, golden_dir):
-    """Against the reference's own outputs.  The reference evaluates the formula with float32 gammaln
-    (its values are off the exact ones by up to ~2e-3 relative, measured below per case), so on rows
-    whose two largest exact probabilities are closer than that noise -- including exact ties, which
-    occur on every third row for some (N, M) -- its argmax is decided by its rounding noise and cannot
-    be reproduced by any other evaluation order.  Gate: argmax bit-exact on EVERY row whose exact
-    top-2 gap exceeds twice the reference's own error; values within that error; overall raw
-    agreement reported and bounded."""
-    from oracle import prior as oprior
+    """Against the reference's own outputs (golden vectors produced by its beta_binomial_prior_distribution).
+    The reference evaluates the formula in float32 (gammaln, adds), and that rounding noise decides the row
+    arg-max near every mode crossover; the kernel reproduces the same float32 arithmetic, so the arg-max must
+    agree on (essentially) every row and the values to float32 exp rounding."""
     g = np.load(os.path.join(golden_dir, "prior_ref.npz"))
     keys = [k for k in g.files if k.startswith("p_")]
     N = [int(k.split("_")[1]) for k in keys]
     M = [int(k.split("_")[2]) for k in keys]
     out, oo = ex.align_prior(N, M)
-    rows = match = clear_rows = 0
+    rows = match = 0
     for i, k in enumerate(keys):
         got = out[oo[i]:oo[i + 1]].view(M[i], N[i]).cpu().numpy()
         ref = g[k]
-        p64 = oprior.prior_f64(N[i], M[i])
-        big = p64 > 1e-6
-        ref_noise = np.abs(ref[big] / p64[big] - 1).max()
-        assert np.abs(got[big] / p64[big] - 1).max() < 1e-5, k            # ours: exact value, rounded once
-        assert np.abs(got[big] / ref[big] - 1).max() <= ref_noise + 1e-5, k  # within the reference's own error
-        same = got.argmax(1) == ref.argmax(1)
-        if N[i] >= 2:
-            srt = np.sort(p64, axis=1)
-            gap = (srt[:, -1] - srt[:, -2]) / srt[:, -1]
-            clear = gap > 2 * ref_noise + 1e-6
-            assert same[clear].all(), k
-            clear_rows += int(clear.sum())
+        big = ref > 1e-30
+        assert np.abs(got[big] / ref[big] - 1).max() < 5e-7, k       # float32 exp: <= 2 ulp apart
+        assert np.abs(got - ref).max() < 1e-7, k
         rows += M[i]
-        match += int(same.sum())
-    assert clear_rows / rows > 0.7
-    assert match / rows >= 0.98, (match, rows)
+        match += int((got.argmax(1) == ref.argmax(1)).sum())
+    assert match / rows >= 0.999, (match, rows)
 
 
 def test_prior_vs_float64_and_scaling(ex):
+    """The float32 evaluation stays within the reference's own error of the exact (float64) value; a
+    non-integer scaling factor takes the float64 lgamma path."""
     from oracle import prior as oprior
     out, oo = ex.align_prior([100, 37], [560, 211])
     for i, (n, m) in enumerate([(100, 560), (37, 211)]):
         got = out[oo[i]:oo[i + 1]].view(m, n).cpu().numpy()
         ref = oprior.prior_f64(n, m)
-        big = ref > 1e-30
-        assert np.abs(got[big] / ref[big] - 1).max() < 1e-5
-        assert np.abs(got.sum(1) - 1).max() < 1e-5
+        ref32 = oprior.beta_binomial_prior_distribution(n, m)
+        big = ref > 1e-6
+        noise = np.abs(ref32[big] / ref[big] - 1).max()
+        assert np.abs(got[big] / ref[big] - 1).max() <= noise * 1.01 + 1e-6
+        assert np.abs(got.sum(1) - 1).max() < 5e-3
+        assert np.array_equal(got.argmax(1), ref32.argmax(1))
     out, oo = ex.align_prior([50], [300], scaling_factor=0.5)
     ref = oprior.prior_f64(50, 300, 0.5)
     got = out.view(300, 50).cpu().numpy()
@@ -384,7 +375,7 @@ def test_properties_full_size_batch(ex):
     for i in (0, 500):
         M, N = int(fo[i + 1] - fo[i]), man[i].text_len
         p = out1["align_prior_matrix"][oo[i]:oo[i + 1]].view(M, N)
-        assert (p.sum(1) - 1).abs().max() < 1e-4
+        assert (p.sum(1) - 1).abs().max() < 5e-3      # float32 evaluation like the reference (row sums drift ~1e-3)
         am = p.argmax(1)
         assert (am[1:] >= am[:-1]).all() and am[0] == 0 and am[-1] == N - 1
 

@@ -130,8 +130,9 @@ def test_emu_prior(golden_dir):
         _, n, m = k.split("_")
         got = hostemu.prior(int(n), int(m))
         ref64 = oprior.prior_f64(int(n), int(m))
-        assert np.abs(got - ref64).max() < 1e-6
-        assert np.abs(got - g[k]).max() < 2e-3
+        assert np.abs(got - ref64).max() < 2e-3          # the reference's float32 noise, reproduced
+        assert np.abs(got - g[k]).max() < 1e-7           # golden = the reference's own output
+        assert np.array_equal(got.argmax(1), g[k].argmax(1))
     got = hostemu.prior(50, 300, 0.5)
     assert np.abs(got - oprior.prior_f64(50, 300, 0.5)).max() < 1e-6
 
