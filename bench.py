@@ -317,7 +317,7 @@ def main():
         import shutil
         import tempfile
         from pathlib import Path
-        from roar_b200.extract_sup_data import CacheWriter
+        from roar_b200.extract_sup_data import ParallelCacheWriter
         nw = min(args.cache_write_utts, n_utts)
         lo = int(offs_h[0]); hi = int(offs_h[nw - 1] + (lens_h[nw - 1] + 3) // 4 * 4)
         bt = ex.batch_from_device(audio[lo:hi], offs_h[:nw] - lo, lens_h[:nw])
@@ -328,21 +328,20 @@ def main():
             names = ("log_mel", "pitch", "voiced_mask", "p_voiced", "energy")
             for k in names:
                 (tmp / k).mkdir()
-            writer = CacheWriter(8)
+            writer = ParallelCacheWriter(min(16, os.cpu_count() or 1))
             t0 = time.perf_counter()
             host = {k: out[k].cpu() for k in names}
             fo = out["frame_off"]
-            for i in range(nw):
-                a, b = int(fo[i]), int(fo[i + 1])
-                for k in names:
-                    ten = host[k][N_MELS * a:N_MELS * b].view(1, N_MELS, b - a) if k == "log_mel" else host[k][a:b]
-                    writer.submit(ten.clone(), tmp / k / f"utt{i}.pt")
+            jobs = [(k, int(fo[i]), int(fo[i + 1]), str(tmp / k / f"utt{i}.pt")) for i in range(nw) for k in names]
+            writer.submit_batch(host, jobs, N_MELS)
             writer.drain()
             dt = time.perf_counter() - t0
+            writer.close()
             cache_write = {"utterances": nw, "files": 5 * nw, "seconds": dt, "files_per_s": 5 * nw / dt,
                            "audio_s_per_s": float(lens_h[:nw].sum()) / SR / dt,
+                           "writer_processes": min(16, os.cpu_count() or 1),
                            "note": "D2H + torch.save of the five cached types through the CLI's writer pool "
-                                   "(8 threads, temp file + rename); outside the timed extraction region"}
+                                   "(worker processes over shared memory, temp file + rename); outside the timed extraction region"}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
         del out

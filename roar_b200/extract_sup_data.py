@@ -48,7 +48,7 @@ DEFAULTS = {
         "ignore_file": None, "trim": False, "pitch_fmin": PITCH_FMIN_C2, "pitch_fmax": PITCH_FMAX_C7,
     },
     "batch_audio_seconds": 4000.0,   # audio per device call (bounds the Viterbi scratch)
-    "writer_threads": 8,
+    "writer_processes": None,        # worker processes writing the .pt cache (default: min(16, cores))
 }
 
 
@@ -316,6 +316,58 @@ class CacheWriter:
         self.futures = []
 
 
+def _save_range(args):
+    """Worker: write the cache files of utterances [lo, hi) of one batch (flat host tensors in shared memory)."""
+    host, jobs, n_mels = args
+    torch.set_num_threads(1)
+    n = 0
+    for t, a, e, path in jobs:
+        if t == "log_mel":
+            ten = host[t][n_mels * a: n_mels * e].view(1, n_mels, e - a).clone()
+        else:
+            ten = host[t][a:e].clone()
+        CacheWriter._save(ten, Path(path))
+        n += 1
+    return n
+
+
+class ParallelCacheWriter:
+    """``torch.save`` of ~5 small files per utterance is pickling-bound (GIL), so a thread pool tops out at a few
+    thousand files/s; this writer hands contiguous utterance ranges of a batch to worker PROCESSES, the flat
+    host tensors travelling once per batch through shared memory."""
+
+    def __init__(self, processes: int):
+        import torch.multiprocessing as mp      # tensors in shared memory travel by handle, not by value
+        self.n = max(1, processes)
+        self.pool = mp.get_context("fork").Pool(self.n) if self.n > 1 else None
+        self.pending = []
+
+    def submit_batch(self, host: Dict[str, torch.Tensor], jobs: List[tuple], n_mels: int):
+        """jobs: (type, frame_begin, frame_end, path) per file, grouped by utterance order."""
+        if not jobs:
+            return
+        if self.pool is None:
+            _save_range((host, jobs, n_mels))
+            return
+        for t in host.values():
+            t.share_memory_()
+        per = (len(jobs) + self.n - 1) // self.n
+        for lo in range(0, len(jobs), per):
+            self.pending.append(self.pool.apply_async(_save_range, ((host, jobs[lo:lo + per], n_mels),)))
+
+    def drain(self):
+        for r in self.pending:
+            r.get()
+        self.pending = []
+
+    def close(self):
+        self.drain()
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
+
+
 # ------------------------------------------------------------------------------------ main
 def run(cfg: dict) -> Optional[Dict[str, float]]:
     import torch.distributed as dist
@@ -325,6 +377,8 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # writer processes are forked before this process creates its CUDA context
+    writer = ParallelCacheWriter(int(cfg.get("writer_processes") or min(16, (os.cpu_count() or 1) // max(1, world))))
     torch.cuda.set_device(local_rank)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -357,7 +411,6 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
     spk_index = {s: i + 1 for i, s in enumerate(speakers)}      # group 0 = "default" (all)
     stats = empty_partials(len(speakers) + 1)
 
-    writer = CacheWriter(int(cfg.get("writer_threads", 8)))
     todo, todo_ids = [], []
     pitch_types = [t for t in ("pitch", "voiced_mask", "p_voiced") if t in types]
     for i in mine:
@@ -404,20 +457,16 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
         host = {k: out[k].cpu() for k in SUP_TYPES_ON_DISK if k in out and out[k] is not None and k in folders}
         fo = out.get("frame_off")
         pfo = out.get("pitch_frame_off")
+        jobs = []
         for n, k in enumerate(b):
             uid, missing = todo_ids[k]
             for t in missing:
-                if t == "log_mel":
-                    a, e = int(fo[n]), int(fo[n + 1])
-                    ten = host[t][scfg.n_mels * a: scfg.n_mels * e].view(1, scfg.n_mels, e - a).clone()
-                elif t == "energy":
-                    ten = host[t][int(fo[n]): int(fo[n + 1])].clone()
-                else:
-                    ten = host[t][int(pfo[n]): int(pfo[n + 1])].clone()
-                writer.submit(ten, folders[t] / f"{uid}.pt")
+                off = fo if t in ("log_mel", "energy") else pfo
+                jobs.append((t, int(off[n]), int(off[n + 1]), str(folders[t] / f"{uid}.pt")))
+        writer.submit_batch(host, jobs, scfg.n_mels)
         for i in idx:
             wavs.pop(i, None)
-    writer.drain()
+    writer.close()
 
     stats = allreduce_partials(stats.cuda()).cpu() if world > 1 else stats
     result = stats_from_partials(stats[0])

@@ -6,6 +6,7 @@ Mirrors what ``TTSDataset.__getitem__`` computes per utterance
 for device memory and streams only; all arithmetic happens in the CUDA library.
 """
 import ctypes
+from contextlib import nullcontext as _nullcontext
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -68,6 +69,8 @@ class SupDataExtractor:
          self.pyin_hop, self.pyin_win, self.kmax, self.n_transition_rows) = [int(x) for x in geo]
         self._ws: Optional[torch.Tensor] = None
         self.kernel_launches = 0  # launches of our kernels issued through this object
+        self._side = None
+        self._ws_side = None
 
     def __del__(self):
         try:
@@ -140,6 +143,11 @@ class SupDataExtractor:
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
 
     # ------------------------------------------------------------------ kernels
     def log_mel_energy(self, batch: PackedBatch, want_log_mel: bool = True, want_energy: bool = True):
@@ -246,22 +254,44 @@ class SupDataExtractor:
         """All supplementary data of one packed batch.  Returns flat device tensors + host offsets."""
         types = set(types)
         out: Dict[str, object] = {}
-        if "log_mel" in types or "energy" in types or "align_prior_matrix" in types:
-            lm, en, fo = self.log_mel_energy(batch, "log_mel" in types, "energy" in types) \
-                if ("log_mel" in types or "energy" in types) else (None, None, None)
-            if fo is None:
-                fo = np.concatenate([[0], np.cumsum(self.num_frames(batch.lens_host))])
-            out["log_mel"], out["energy"], out["frame_off"] = lm, en, fo
-        if "align_prior_matrix" in types:
-            if text_lens is None:
-                raise ValueError("align_prior_matrix needs text_lens")
-            mel_lens = np.diff(out["frame_off"])
-            out["align_prior_matrix"], out["prior_off"] = self.align_prior(text_lens, mel_lens)
-        if types & {"pitch", "voiced_mask", "p_voiced"}:
+        want_pitch = bool(types & {"pitch", "voiced_mask", "p_voiced"})
+        want_spec = bool(types & {"log_mel", "energy", "align_prior_matrix"})
+        # The spectral kernels and the pYIN chain are independent: when both are requested the spectral
+        # side runs on a second stream (its own workspace), forked from / joined to the caller's stream,
+        # so its CTAs fill the SMs the latency-bound Viterbi leaves idle.
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_stream() if (want_pitch and want_spec and batch.n_utts > 0) else None
+        if side is not None:
+            side.wait_stream(main)
+        if want_spec:
+            with torch.cuda.stream(side) if side is not None else _nullcontext():
+                if side is not None:
+                    self._ws, self._ws_side = self._ws_side, self._ws      # spectral side uses its own workspace
+                try:
+                    lm, en, fo = self.log_mel_energy(batch, "log_mel" in types, "energy" in types) \
+                        if ("log_mel" in types or "energy" in types) else (None, None, None)
+                    if fo is None:
+                        fo = np.concatenate([[0], np.cumsum(self.num_frames(batch.lens_host))])
+                    out["log_mel"], out["energy"], out["frame_off"] = lm, en, fo
+                    if "align_prior_matrix" in types:
+                        if text_lens is None:
+                            raise ValueError("align_prior_matrix needs text_lens")
+                        mel_lens = np.diff(out["frame_off"])
+                        out["align_prior_matrix"], out["prior_off"] = self.align_prior(text_lens, mel_lens)
+                finally:
+                    if side is not None:
+                        self._ws, self._ws_side = self._ws_side, self._ws
+        if want_pitch:
             f0, vf, vp, pfo = self.pyin(batch)
             out["pitch"], out["voiced_mask"], out["p_voiced"], out["pitch_frame_off"] = f0, vf, vp, pfo
             if stats is not None:
                 self.pitch_partials(f0, stats)
+        if side is not None:
+            main.wait_stream(side)
+            for k in ("log_mel", "energy", "align_prior_matrix"):
+                t = out.get(k)
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(main)      # allocated on the side stream, consumed on the caller's
         return out
 
 

@@ -215,3 +215,23 @@ def test_pitch_normalisation_and_stats_selection(tmp_path):
         du.select_pitch_stats({}, pitch_stats={"3": stats["7"]})
     with pytest.raises(ValueError):
         du.select_pitch_stats({})
+
+
+def test_parallel_cache_writer(tmp_path):
+    """Worker processes write exactly the tensors the reference saves: CPU float32, log_mel [1, n_mels, T]."""
+    import torch
+    from roar_b200.extract_sup_data import ParallelCacheWriter
+    n_mels, T = 4, [3, 5, 2]
+    fo = np.concatenate([[0], np.cumsum(T)])
+    host = {"log_mel": torch.arange(n_mels * fo[-1], dtype=torch.float32), "pitch": torch.arange(fo[-1], dtype=torch.float32)}
+    jobs = [(k, int(fo[i]), int(fo[i + 1]), str(tmp_path / f"{k}_{i}.pt")) for i in range(3) for k in host]
+    for procs in (1, 3):
+        w = ParallelCacheWriter(procs)
+        w.submit_batch({k: v.clone() for k, v in host.items()}, jobs, n_mels)
+        w.close()
+        for i in range(3):
+            lm = torch.load(tmp_path / f"log_mel_{i}.pt")
+            assert lm.shape == (1, n_mels, T[i]) and lm.dtype == torch.float32
+            assert torch.equal(lm.flatten(), host["log_mel"][n_mels * fo[i]:n_mels * fo[i + 1]])
+            assert torch.equal(torch.load(tmp_path / f"pitch_{i}.pt"), host["pitch"][fo[i]:fo[i + 1]])
+            assert lm.untyped_storage().nbytes() == lm.numel() * 4      # compact storage, not the whole batch
