@@ -424,6 +424,10 @@ def main():
         "x_realtime_per_gpu": value / world,
         "gpu_launches": launches, "clocks": clocks,
         "kernels_ms_per_step": {k: round(v, 4) for k, v in per.items() if v > 0},
+        "kernels_note": "CUDA-event brackets on each kernel's launching stream inside the timed region; the spectral "
+                        "kernels (stft_mel, prior) run on a side stream concurrently with the pYIN chain, so a bracket "
+                        "can include time queued behind the other stream (tile_offsets, pyin_energy) and the brackets "
+                        "sum to more than ms_per_step",
         "roofline": roofline,
         "roofline_kernels": roofline_kernels,
         "roofline_path": {"bound": "hbm", "achieved": path_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak,
