@@ -94,7 +94,7 @@ typedef struct roar_sup_handle roar_sup_handle;
 /* kernel ids for the optional per-kernel timing below */
 enum roar_sup_kernel { ROAR_K_TILE_OFFSETS = 0, ROAR_K_STFT_MEL = 1, ROAR_K_PYIN_CMND = 2, ROAR_K_PYIN_PROBS = 3,
                        ROAR_K_LEN_SORT = 4, ROAR_K_VITERBI = 5, ROAR_K_BACKTRACK = 6, ROAR_K_PRIOR = 7,
-                       ROAR_K_STATS = 8, ROAR_K_FBANK_NORM = 9, ROAR_K_PYIN_ENERGY = 10, ROAR_K_COUNT = 11 };
+                       ROAR_K_STATS = 8, ROAR_K_FBANK_NORM = 9, ROAR_K_PYIN_ENERGY = 10, ROAR_K_COUNT = 11 };  /* roar_sup_trim is not timed */
 
 /* Fill cfg with the reference's extraction defaults
  * (scripts/dataset_processing/tts/rasa/ds_conf/ds_for_fastpitch_align.yaml:12-27). */
@@ -169,6 +169,16 @@ int roar_sup_align_prior_interp(roar_sup_handle* h, const int32_t* d_text_len, c
                                 int32_t n_utts, const int64_t* d_out_off, int32_t max_mel_len,
                                 int32_t round_mel_len_to, int32_t round_text_len_to, float* d_prior,
                                 void* stream);
+
+/* Silence trimming: replaces librosa.effects.trim(samples, top_db, ref, frame_length, hop_length) as called by
+ * AudioSegment (asr/parts/preprocessing/segment.py:76-88; TTSDataset forwards trim_* at dataset.py:613-617).
+ * Writes [start, end) sample indices per utterance (relative to the utterance start); the caller narrows
+ * sample_off / sample_len, no audio is copied.  ref_value <= 0 selects ref = np.max (the reference default).
+ * Utterances of more than 24 576 trim frames are rejected. */
+int roar_sup_trim(roar_sup_handle* h, const float* d_audio, const int64_t* d_sample_off,
+                  const int32_t* d_sample_len, int32_t n_utts, int32_t max_samples_per_utt, double top_db,
+                  double ref_value, int32_t frame_length, int32_t hop_length, int64_t* d_start, int64_t* d_end,
+                  void* stream);
 
 /* Partial pitch statistics over f0 != 0: replaces get_pitch_stats
  * (scripts/dataset_processing/tts/extract_sup_data.py:8-13, 29-30).

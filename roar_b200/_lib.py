@@ -16,7 +16,7 @@ SYMBOLS = [
     "roar_sup_host_pyin_beta_probs", "roar_sup_workspace_bytes", "roar_sup_logmel_energy",
     "roar_sup_pyin", "roar_sup_align_prior", "roar_sup_align_prior_interp", "roar_sup_pitch_partials_init", "roar_sup_pitch_partials",
     "roar_sup_pitch_partials_grouped", "roar_fbank_out_frames", "roar_fbank_forward",
-    "roar_sup_set_profiling", "roar_sup_profile_read",
+    "roar_sup_set_profiling", "roar_sup_profile_read", "roar_sup_trim",
 ]
 
 _lib = None
@@ -59,6 +59,7 @@ def load():
     lib.roar_sup_pyin.argtypes = [vp, vp, vp, vp, i32, vp, i64, i32, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.roar_sup_align_prior.argtypes = [vp, vp, vp, i32, vp, i32, f64, vp, vp]
     lib.roar_sup_align_prior_interp.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, vp]
+    lib.roar_sup_trim.argtypes = [vp, vp, vp, vp, i32, i32, f64, f64, i32, i32, vp, vp, vp]
     lib.roar_sup_pitch_partials_init.argtypes = [vp, vp, i32, vp]
     lib.roar_sup_pitch_partials.argtypes = [vp, vp, i64, vp, vp]
     lib.roar_sup_pitch_partials_grouped.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]

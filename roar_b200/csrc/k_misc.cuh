@@ -127,6 +127,95 @@ __global__ void __launch_bounds__(256) k_align_prior(const PriorParams p) {
   }
 }
 
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------ K7 silence trim
+// librosa.effects.trim(samples, top_db, ref, frame_length, hop_length) as called by AudioSegment
+// (asr/parts/preprocessing/segment.py:76-88): frame RMS (center=True, zero padding), dB relative to
+// the reference (np.max of the RMS by default), first / last frame above -top_db ->
+// [start, end) = [f0 * hop, min(L, (f1 + 1) * hop)).  One CTA per utterance, one warp per frame, the
+// frame powers kept in shared memory (float64 sums of float32 squares).
+struct TrimParams {
+  const float* audio;
+  const int64_t* sample_off;
+  const int32_t* sample_len;
+  int32_t n_utts, frame_length, hop_length, max_frames;
+  double top_db, ref_value;     // ref_value <= 0: np.max over the utterance's frames
+  int64_t* start;
+  int64_t* end;
+};
+HD bool trim_is_loud(double power, double ref_power, double top_db) {
+  const double amin = 1e-10;     // amin ** 2 with amin = 1e-5 (amplitude_to_db)
+  const double db = 10.0 * log10(power > amin ? power : amin) - 10.0 * log10(ref_power > amin ? ref_power : amin);
+  return db > -top_db;
+}
+// mean square of frame f (zero-padded by frame_length / 2 on both sides), lanes stride the samples
+HD double trim_frame_power_part(const float* y, int L, int frame_length, int hop, int f, int lane, int nl) {
+  const int64_t s0 = (int64_t)f * hop - frame_length / 2;
+  double acc = 0.0;
+  for (int i = lane; i < frame_length; i += nl) {
+    const int64_t q = s0 + i;
+    if (q >= 0 && q < L) { const double v = y[q]; acc += v * v; }
+  }
+  return acc;
+}
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(256) k_trim(const TrimParams p) {
+  extern __shared__ __align__(16) double t_pow[];      // [max_frames]
+  __shared__ double s_wmax[8];
+  __shared__ int s_first[8], s_last[8];
+  const int utt = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int L = p.sample_len[utt];
+  const float* y = p.audio + p.sample_off[utt];
+  const int T = 1 + L / p.hop_length;
+  double wmax = 0.0;
+  for (int f = warp; f < T; f += nwarp) {
+    double acc = trim_frame_power_part(y, L, p.frame_length, p.hop_length, f, lane, 32);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const double pw = acc / (double)p.frame_length;
+    if (lane == 0) t_pow[f] = pw;
+    wmax = pw > wmax ? pw : wmax;
+  }
+  if (lane == 0) s_wmax[warp] = wmax;
+  __syncthreads();
+  double ref_power = p.ref_value * p.ref_value;
+  if (p.ref_value <= 0.0) {
+    ref_power = 0.0;
+    for (int w = 0; w < nwarp; ++w) ref_power = s_wmax[w] > ref_power ? s_wmax[w] : ref_power;
+    // ref = np.max(rms): (sqrt(max power)) ** 2 in the reference; sqrt then square in float64 here
+    const double r = sqrt(ref_power);
+    ref_power = r * r;
+  }
+  int first = 0x7fffffff, last = -1;
+  for (int f = tid; f < T; f += blockDim.x) {
+    // the reference squares the float32 RMS again: rms = sqrt(power) (float32), power' = rms ** 2
+    const float rms32 = sqrtf((float)t_pow[f]);
+    const double pw = (double)rms32 * (double)rms32;
+    if (trim_is_loud(pw, ref_power, p.top_db)) { first = f < first ? f : first; last = f > last ? f : last; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int a = __shfl_xor_sync(0xffffffffu, first, o), b = __shfl_xor_sync(0xffffffffu, last, o);
+    first = a < first ? a : first; last = b > last ? b : last;
+  }
+  if (lane == 0) { s_first[warp] = first; s_last[warp] = last; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 0; w < nwarp; ++w) { first = s_first[w] < first ? s_first[w] : first; last = s_last[w] > last ? s_last[w] : last; }
+    int64_t st = 0, en = 0;
+    if (last >= 0) {
+      st = (int64_t)first * p.hop_length;
+      en = (int64_t)(last + 1) * p.hop_length;
+      if (en > L) en = L;
+    }
+    p.start[utt] = st; p.end[utt] = en;
+  }
+}
+#endif  // __CUDACC__
+
+#ifdef __CUDACC__
 // ------------------------------------------------------------------------------------ K5 stats
 // get_pitch_stats (scripts/dataset_processing/tts/extract_sup_data.py:8-13): mean / unbiased std /
 // min / max over pitch != 0.  Produces float64 partials (sum, sumsq, count, min, max) that the ranks

@@ -525,6 +525,27 @@ int roar_sup_align_prior_interp(roar_sup_handle* h, const int32_t* d_text_len, c
   return 0;
 }
 
+int roar_sup_trim(roar_sup_handle* h, const float* d_audio, const int64_t* d_sample_off,
+                  const int32_t* d_sample_len, int32_t n_utts, int32_t max_samples_per_utt, double top_db,
+                  double ref_value, int32_t frame_length, int32_t hop_length, int64_t* d_start, int64_t* d_end,
+                  void* stream) {
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
+  if (n_utts <= 0) return 0;
+  if (!d_audio || !d_sample_off || !d_sample_len || !d_start || !d_end) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (frame_length < 1 || hop_length < 1) return fail(ROAR_ERR_INVALID_ARG, "trim frame / hop length must be positive");
+  const int64_t max_frames = 1 + (int64_t)max_samples_per_utt / hop_length;
+  if (max_frames > 24576) return fail(ROAR_ERR_UNSUPPORTED, "utterance too long for roar_sup_trim (more than 24576 trim frames)");
+  TrimParams p;
+  p.audio = d_audio; p.sample_off = d_sample_off; p.sample_len = d_sample_len; p.n_utts = n_utts;
+  p.frame_length = frame_length; p.hop_length = hop_length; p.max_frames = (int32_t)max_frames;
+  p.top_db = top_db; p.ref_value = ref_value; p.start = d_start; p.end = d_end;
+  const size_t smem = sizeof(double) * (size_t)max_frames;
+  CUDA_TRY(cudaFuncSetAttribute(k_trim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem - 2048));   // it also has static arrays
+  k_trim<<<n_utts, 256, smem, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int roar_sup_pitch_partials_init(roar_sup_handle* h, double* d_out, int32_t n_groups, void* stream) {
   if (!h || !d_out || n_groups <= 0) return fail(ROAR_ERR_INVALID_ARG, "bad argument");
   k_stats_init<<<(n_groups + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_out, n_groups);

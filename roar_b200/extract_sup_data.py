@@ -16,8 +16,10 @@ Differences, on purpose: sup types are addressed by NAME (the reference unpacks 
 positionally); statistics are accumulated in float64 and all-reduced across
 ranks; ``pitch_stats.json`` (``default`` + per speaker, the format ``pitch_stats_path`` reads,
 ``dataset.py:485-487, 720-733``) is written next to the cache.
-Out of scope: resampling and trimming -- the audio must already be at
-``dataset.sample_rate``; wav decoding uses ``scipy.io.wavfile`` on the host.
+``dataset.trim=true`` (+ ``trim_ref``, ``trim_top_db``, ``trim_frame_length``, ``trim_hop_length``) runs
+``librosa.effects.trim`` on the GPU (``roar_sup_trim``).  Out of scope:
+resampling -- the audio must already be at ``dataset.sample_rate``; wav decoding uses
+``scipy.io.wavfile`` on the host.
 """
 import json
 import os
@@ -389,8 +391,12 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
             raise NotImplementedError(f"sup_data_type {t!r} is outside the accelerated path "
                                       f"(supported: {VALID_SUP_TYPES})")
     d = cfg["dataset"]
+    trim_kw = None
     if d.get("trim"):
-        raise NotImplementedError("dataset.trim=true is outside the accelerated path (SURVEY.md section 8f, N3)")
+        # librosa.effects.trim with the TTSDataset defaults (dataset.py:285-291); trim_ref=None means np.max
+        trim_kw = dict(top_db=d.get("trim_top_db") if d.get("trim_top_db") is not None else 60,
+                       ref=d.get("trim_ref"), frame_length=d.get("trim_frame_length") or 2048,
+                       hop_length=d.get("trim_hop_length") or 512)
     scfg = sup_config_from(cfg)
     ex = SupDataExtractor(scfg)
     items = read_manifest(cfg["manifest_filepath"], d.get("min_duration"), d.get("max_duration"), d.get("ignore_file"))
@@ -439,6 +445,8 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
     for b in make_batches(lengths, int(float(cfg.get("batch_audio_seconds", 4000.0)) * scfg.sample_rate)):
         idx = [todo[k] for k in b]
         batch = ex.pack([get_wav(i) for i in idx])
+        if trim_kw is not None:
+            batch = ex.trim(batch, **trim_kw)
         need = set().union(*[todo_ids[k][1] for k in b])
         want = [t for t in types if t in need or t == "align_prior_matrix"]
         if pitch_types and need & set(pitch_types):

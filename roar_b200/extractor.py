@@ -123,6 +123,26 @@ class SupDataExtractor:
                            torch.from_numpy(np.ascontiguousarray(lens, dtype=np.int32)).to(self.device),
                            np.asarray(lens, dtype=np.int64), np.asarray(offs, dtype=np.int64))
 
+    def trim(self, batch: PackedBatch, top_db: float = 60.0, ref: Optional[float] = None, frame_length: int = 2048,
+             hop_length: int = 512) -> PackedBatch:
+        """``librosa.effects.trim`` for every utterance of the batch (``segment.py:76-88``): returns a batch
+        over the SAME audio buffer with narrowed offsets / lengths (``ref=None`` = ``np.max`` like the
+        reference's ``trim_ref`` default).  ``batch.trim_bounds`` holds the [start, end) pairs."""
+        if batch.n_utts == 0:
+            return batch
+        n = batch.n_utts
+        st = torch.empty(n, dtype=torch.int64, device=self.device)
+        en = torch.empty(n, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.roar_sup_trim(self._h, _ptr(batch.audio), _ptr(batch.sample_off), _ptr(batch.sample_len), n,
+                                          int(batch.lens_host.max()), float(top_db), float(ref) if ref else 0.0,
+                                          int(frame_length), int(hop_length), _ptr(st), _ptr(en), self._stream()))
+        self.kernel_launches += 1
+        st_h, en_h = st.cpu().numpy(), en.cpu().numpy()
+        out = PackedBatch(batch.audio, batch.sample_off + st, (en - st).to(torch.int32), en_h - st_h,
+                          batch.offs_host + st_h)
+        out.trim_bounds = np.stack([st_h, en_h], axis=1)
+        return out
+
     def _check_lengths(self, batch: PackedBatch, what: str):
         pad = (self.cfg.n_fft - self.cfg.hop) // 2 if self.cfg.exact_pad else self.cfg.n_fft // 2
         if batch.n_utts and int(batch.lens_host.min()) <= pad:

@@ -72,3 +72,13 @@ def prior_interp(text_len, mel_len, round_mel=50, round_text=10):
                                 ctypes.c_int32(round_text), out.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0
     return out
+
+
+def trim(audio, top_db=60.0, ref_value=0.0, frame_length=2048, hop_length=512):
+    audio = _f32(audio)
+    out = np.zeros(2, np.int64)
+    rc = lib().emu_trim(audio.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(audio)), ctypes.c_double(top_db),
+                        ctypes.c_double(ref_value), ctypes.c_int32(frame_length), ctypes.c_int32(hop_length),
+                        out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return int(out[0]), int(out[1])

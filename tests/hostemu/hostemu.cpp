@@ -281,6 +281,29 @@ int emu_prior(int32_t N, int32_t M, double scaling, float* out) {
   return 0;
 }
 
+int emu_trim(const float* y, int64_t L, double top_db, double ref_value, int32_t frame_length, int32_t hop,
+             int64_t* out2) {
+  const int T = (int)(1 + L / hop);
+  std::vector<double> pw(T);
+  double mx = 0.0;
+  for (int f = 0; f < T; ++f) {
+    double acc = 0.0;
+    for (int l = 0; l < 32; ++l) acc += trim_frame_power_part(y, (int)L, frame_length, hop, f, l, 32);
+    pw[f] = acc / frame_length;
+    if (pw[f] > mx) mx = pw[f];
+  }
+  double ref_power = ref_value * ref_value;
+  if (ref_value <= 0.0) { const double r = std::sqrt(mx); ref_power = r * r; }
+  int first = 0x7fffffff, last = -1;
+  for (int f = 0; f < T; ++f) {
+    const float rms32 = sqrtf((float)pw[f]);
+    if (trim_is_loud((double)rms32 * (double)rms32, ref_power, top_db)) { if (f < first) first = f; if (f > last) last = f; }
+  }
+  out2[0] = 0; out2[1] = 0;
+  if (last >= 0) { out2[0] = (int64_t)first * hop; out2[1] = (int64_t)(last + 1) * hop; if (out2[1] > L) out2[1] = L; }
+  return 0;
+}
+
 int emu_prior_interp(int32_t text_len, int32_t mel_len, int32_t round_mel, int32_t round_text, float* out) {
   std::vector<double> lf(8192);
   for (size_t i = 0; i < lf.size(); ++i) lf[i] = std::lgamma((double)i + 1.0);

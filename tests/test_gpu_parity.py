@@ -219,6 +219,32 @@ def test_handles_with_different_geometries_coexist(ex, c1):
     assert torch.equal(before[0], after[0]) and torch.isfinite(lm[0]).all()
 
 
+def test_trim_vs_oracle_and_trimmed_extraction(ex, c1):
+    """roar_sup_trim (librosa.effects.trim, segment.py:76-88) and extraction over the narrowed batch."""
+    from oracle import spec as ospec
+    from oracle import trim as otrim
+    from roar_b200.extractor import split_frames
+    man, wavs = c1
+    rng = np.random.default_rng(5)
+    padded = [np.concatenate([1e-5 * rng.standard_normal(int(rng.integers(0, 7000))).astype(np.float32), w,
+                              np.zeros(int(rng.integers(0, 7000)), np.float32)]) for w in wavs[:8]]
+    b = ex.pack(padded)
+    for kw in (dict(), dict(top_db=30), dict(top_db=40, ref=0.5, frame_length=1024, hop_length=256)):
+        tb = ex.trim(b, **kw)
+        for i, y in enumerate(padded):
+            _, (s, e) = otrim.trim(y, **kw)
+            assert tuple(tb.trim_bounds[i]) == (s, e), (i, kw)
+    tb = ex.trim(b)
+    lm, en, fo = ex.log_mel_energy(tb)
+    fb = ex.mel_filterbank()
+    for i, y in enumerate(padded):
+        s, e = tb.trim_bounds[i]
+        ref = ospec.get_log_mel(y[s:e], fb).numpy()[0]
+        got = split_frames(lm, fo, 80)[i].cpu().numpy()
+        assert got.shape == ref.shape
+        assert (np.abs(got - ref) / np.maximum(1, np.abs(ref))).max() <= 1e-4
+
+
 def test_empty_batch_and_too_short_input(ex):
     """Edge cases: an empty shard is a no-op; audio not longer than the reflect pad is rejected like
     torch.stft does in the reference (dataset.py:324-333)."""

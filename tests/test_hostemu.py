@@ -186,3 +186,21 @@ def test_emu_pyin_block_geometries(kw, okw):
     assert cm.shape == info["yin_frames"].T.shape
     assert np.abs(cm - info["yin_frames"].T).max() < 1e-9
     assert np.array_equal(st, info["states"]) and np.abs(vp - ovp).max() < 1e-6
+
+
+def test_emu_trim_equals_oracle():
+    """librosa.effects.trim as AudioSegment calls it (segment.py:76-88): leading / trailing silence, both
+    thresholds, a fixed reference, digital silence (everything is 'loud' relative to itself)."""
+    from oracle import trim as otrim
+    rng = np.random.default_rng(3)
+    for i in range(12):
+        w = _wav(i % 6, 20000 + 777 * i)
+        y = np.concatenate([1e-5 * rng.standard_normal(int(rng.integers(0, 9000))).astype(np.float32), w,
+                            np.zeros(int(rng.integers(0, 9000)), np.float32)])
+        for top_db in (60, 25):
+            _, se = otrim.trim(y, top_db=top_db)
+            assert hostemu.trim(y, top_db) == se
+        _, se = otrim.trim(y, top_db=40, ref=0.5, frame_length=1024, hop_length=256)
+        assert hostemu.trim(y, 40, 0.5, 1024, 256) == se
+    z = np.zeros(5000, np.float32)
+    assert hostemu.trim(z) == otrim.trim(z)[1] == (0, 5000)
