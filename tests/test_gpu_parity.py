@@ -552,3 +552,34 @@ def test_featurizers_vs_oracle_and_cli(tmp_path, c1):
         assert torch.load(feature_dir / "energy" / "spk0" / f"utt{i}.pt").shape == (m.shape[1],)
     loaded = energy.load(entries[0], audio_dir, feature_dir)
     assert set(loaded) == {"energy"}
+
+
+def test_cli_with_trim(tmp_path, capsys):
+    """`dataset.trim=true`: the cache holds the features of the trimmed audio (segment.py:76-88)."""
+    import json
+    from scipy.io import wavfile
+    from oracle import pyin as opyin
+    from oracle import trim as otrim
+    from roar_b200 import extract_sup_data as X, synth
+    rng = np.random.default_rng(9)
+    mf = tmp_path / "m.json"
+    rows, refs = [], []
+    for i in range(3):
+        w = synth.synth_utterance(1234, i, 22050 * 2, 22050, 0)
+        y = np.concatenate([np.zeros(int(rng.integers(2000, 9000)), np.float32), w,
+                            1e-5 * rng.standard_normal(int(rng.integers(2000, 9000))).astype(np.float32)])
+        p = tmp_path / "w" / f"u{i}.wav"
+        p.parent.mkdir(exist_ok=True)
+        wavfile.write(p, 22050, y)
+        rows.append(json.dumps({"audio_filepath": str(p), "duration": len(y) / 22050, "text": "abc"}))
+        refs.append(otrim.trim(y, top_db=50)[0])
+    mf.write_text("\n".join(rows) + "\n")
+    sup = tmp_path / "sup"
+    X.main([f"manifest_filepath={mf}", f"sup_data_path={sup}", "sup_data_types=[align_prior_matrix,pitch,energy]",
+            "dataset.trim=true", "dataset.trim_top_db=50"])
+    capsys.readouterr()
+    for i, yt in enumerate(refs):
+        pitch = torch.load(sup / "pitch" / f"u{i}.pt").numpy()
+        assert len(yt) < 22050 * 2 + 18000 and pitch.shape == (1 + len(yt) // 256,)
+        of0, _, _ = opyin.pyin(yt, FMIN, FMAX, sr=22050, frame_length=1024, fill_na=0.0)
+        assert np.array_equal(pitch, of0.astype(np.float32))
