@@ -202,6 +202,14 @@ int roar_fbank_forward(roar_sup_handle* h, const float* d_x, const int64_t* d_le
                        int64_t Lmax, float* d_out, int64_t* d_out_len, void* d_workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Backward of roar_fbank_forward for FilterbankFeatures(use_grads=True) (features.py:329-331,408-410; used by
+ * the mel losses of tts/models/jets.py:175-177, hifigan.py:56-58, bigvgan.py:57-59, roar_tts.py:174-176):
+ * d_grad_out [B, n_mels, Tpad] -> d_grad_x [B, Lmax] (overwritten).  The forward spectrum is recomputed.
+ * Requires normalize = NONE and no pre-emphasis (the reference's grad configurations). */
+int roar_fbank_backward(roar_sup_handle* h, const float* d_x, const int64_t* d_len, int32_t B, int64_t Lmax,
+                        const float* d_grad_out, float* d_grad_x, void* d_workspace, size_t workspace_bytes,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ SYMBOLS = [
     "roar_sup_host_pyin_beta_probs", "roar_sup_workspace_bytes", "roar_sup_logmel_energy",
     "roar_sup_pyin", "roar_sup_align_prior", "roar_sup_align_prior_interp", "roar_sup_pitch_partials_init", "roar_sup_pitch_partials",
     "roar_sup_pitch_partials_grouped", "roar_fbank_out_frames", "roar_fbank_forward",
-    "roar_sup_set_profiling", "roar_sup_profile_read", "roar_sup_trim",
+    "roar_sup_set_profiling", "roar_sup_profile_read", "roar_sup_trim", "roar_fbank_backward",
 ]
 
 _lib = None
@@ -66,6 +66,7 @@ def load():
     lib.roar_fbank_out_frames.argtypes = [vp, i64]
     lib.roar_fbank_out_frames.restype = i64
     lib.roar_fbank_forward.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.roar_fbank_backward.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp, ctypes.c_size_t, vp]
     lib.roar_sup_set_profiling.argtypes = [vp, ctypes.c_int]
     lib.roar_sup_profile_read.argtypes = [vp, vp, vp, ctypes.c_int]
     if lib.roar_sup_abi_version() != 1:

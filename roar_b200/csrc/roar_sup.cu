@@ -14,6 +14,7 @@
 #include "k_misc.cuh"
 #include "k_pyin_front.cuh"
 #include "k_stft_mel.cuh"
+#include "k_stft_bwd.cuh"
 #include "k_viterbi.cuh"
 #include "tables.hpp"
 
@@ -124,6 +125,18 @@ static PyinParams pyin_params_base(const roar_sup_handle* h) {
   p.thresholds = h->d_thr; p.beta_probs = h->d_beta; p.beta_cum = h->d_beta_cum;
   p.boltz_exp = h->d_bexp; p.boltz_fact = h->d_bfact;
   return p;
+}
+
+static void launch_stft_bwd(unsigned grid, size_t smem, cudaStream_t st, const StftBwdParams& q) {
+  switch (q.f.M) {
+    case 32: k_stft_mel_bwd<5><<<grid, 256, smem, st>>>(q); break;
+    case 64: k_stft_mel_bwd<6><<<grid, 256, smem, st>>>(q); break;
+    case 128: k_stft_mel_bwd<7><<<grid, 256, smem, st>>>(q); break;
+    case 256: k_stft_mel_bwd<8><<<grid, 256, smem, st>>>(q); break;
+    case 512: k_stft_mel_bwd<9><<<grid, 256, smem, st>>>(q); break;
+    case 1024: k_stft_mel_bwd<10><<<grid, 256, smem, st>>>(q); break;
+    default: k_stft_mel_bwd<11><<<grid, 256, smem, st>>>(q); break;
+  }
 }
 
 static void launch_stft(const roar_sup_handle* h, unsigned grid, cudaStream_t st, const StftParams& p) {
@@ -242,6 +255,13 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
     CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
     CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
     CUDA_TRY(cudaFuncSetAttribute(k_stft_mel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel_bwd<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel_bwd<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel_bwd<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel_bwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel_bwd<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel_bwd<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_stft_mel_bwd<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
   }
   // ---- K2 / K3 tables
   {
@@ -628,6 +648,47 @@ int roar_fbank_forward(roar_sup_handle* h, const float* d_x, const int64_t* d_le
   np.Tpad = (int32_t)Tpad; np.mode = h->cfg.normalize; np.pad_value = (float)h->cfg.pad_value;
   dim3 grid(np.mode == ROAR_NORM_ALL_FEATURES ? 1 : g.n_mels, B);
   LAUNCH(h, ROAR_K_FBANK_NORM, st, k_fbank_normalize<<<grid, 256, 0, st>>>(np));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int roar_fbank_backward(roar_sup_handle* h, const float* d_x, const int64_t* d_len, int32_t B, int64_t Lmax,
+                        const float* d_grad_out, float* d_grad_x, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
+  if (B <= 0) return 0;
+  if (!d_x || !d_len || !d_grad_out || !d_grad_x) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (h->cfg.has_preemph) return fail(ROAR_ERR_UNSUPPORTED, "roar_fbank_backward: pre-emphasis is not differentiated (the reference's grad configs use preemph=None)");
+  if (h->cfg.normalize != ROAR_NORM_NONE) return fail(ROAR_ERR_UNSUPPORTED, "roar_fbank_backward: normalize must be None (as in the reference's grad configs)");
+  const Geometry& g = h->g;
+  const int64_t pad = h->cfg.exact_pad ? (g.n_fft - g.hop) / 2 : g.n_fft / 2;
+  if (Lmax <= pad) return fail(ROAR_ERR_INVALID_ARG, "input shorter than the reflect padding");
+  const int64_t T_full = roar_sup_num_frames(h, Lmax), Tpad = roar_fbank_out_frames(h, Lmax);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* base = (unsigned char*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { unsigned char* p = base + o; o += a256(bytes); return p; };
+  int64_t* sample_off = (int64_t*)take(sizeof(int64_t) * (B + 1));
+  int32_t* sample_len = (int32_t*)take(sizeof(int32_t) * (B + 1));
+  int64_t* frame_off = (int64_t*)take(sizeof(int64_t) * (B + 1));
+  int32_t* tile_off = (int32_t*)take(sizeof(int32_t) * (B + 1));
+  int64_t* valid = (int64_t*)take(sizeof(int64_t) * (B + 1));
+  if (!d_ws || o + 256 > ws_bytes) return fail(ROAR_ERR_WORKSPACE, "workspace too small for roar_fbank_backward");
+  k_fbank_setup<<<(B + 256) / 256, 256, 0, st>>>(d_len, B, Lmax, T_full, g.n_fft, g.hop, (int32_t)(2 * pad),
+                                                 sample_off, sample_len, frame_off, valid);
+  CUDA_TRY(cudaMemsetAsync(d_grad_x, 0, sizeof(float) * (size_t)B * (size_t)Lmax, st));
+  StftBwdParams q;
+  memset(&q, 0, sizeof(q));
+  q.f = stft_params_base(h);
+  q.f.use_tma = 0;
+  q.f.audio = d_x; q.f.sample_off = sample_off; q.f.sample_len = sample_len; q.f.frame_off = frame_off;
+  q.f.tile_off = tile_off; q.f.n_utts = B;
+  q.f.out_utt_stride = (int64_t)g.n_mels * Tpad; q.f.out_row_stride = Tpad;
+  q.grad_out = d_grad_out; q.valid_len = valid; q.grad_audio = d_grad_x;
+  k_tile_offsets<<<1, 1024, 0, st>>>(frame_off, B, q.f.FT, tile_off);
+  const size_t smem = h->stft_smem + stft_bwd_extra_carve(q.f, nullptr, nullptr);
+  if (smem > h->max_smem) return fail(ROAR_ERR_UNSUPPORTED, "backward tile does not fit in shared memory");
+  const int64_t max_tiles = (T_full * B) / q.f.FT + B;
+  launch_stft_bwd((unsigned)max_tiles, smem, st, q);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

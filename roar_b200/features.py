@@ -4,8 +4,10 @@
 * ``AudioToMelSpectrogramPreprocessor`` <- ``.../audio_preprocessing.py:90-290`` (kwargs-only
   ``forward(input_signal=, length=)`` like the reference's ``@typecheck``-ed module)
 
-Same constructor arguments, same outputs ``(features [B, nfilt, T'], seq_len [B])``.  Scope is the
-no-grad inference/extraction path: ``use_grads=True``, training-time dither / narrow-band
+Same constructor arguments, same outputs ``(features [B, nfilt, T'], seq_len [B])``.
+``use_grads=True`` (the mel-loss preprocessors of JETS / HiFi-GAN / BigVGAN / RoarTTS,
+``tts/models/jets.py:175-177``) is differentiable through ``roar_fbank_backward`` for
+``normalize=None, preemph=None`` -- those models' configuration; training-time dither / narrow-band
 augmentation, ``frame_splicing > 1`` and ``linear_spec=True`` raise instead of silently taking another
 path.
 """
@@ -48,8 +50,9 @@ class FilterbankFeatures(nn.Module):
         if log_zero_guard_type not in ["add", "clamp"]:
             raise ValueError(f"{self} received {log_zero_guard_type} for the log_zero_guard_type parameter. "
                              f"It must be either 'add' or 'clamp'.")
-        if use_grads:
-            raise NotImplementedError("roar_b200.FilterbankFeatures covers the no-grad path only (use_grads=False)")
+        if use_grads and (preemph is not None or normalize is not None):
+            raise NotImplementedError("use_grads=True is differentiated for normalize=None, preemph=None (the "
+                                      "reference's mel-loss configurations: jets.py:175-177, hifigan.py:56-58)")
         if frame_splicing != 1:
             raise NotImplementedError("frame_splicing > 1 is outside the accelerated path")
         if isinstance(normalize, dict):
@@ -79,7 +82,7 @@ class FilterbankFeatures(nn.Module):
             sample_rate=sample_rate, n_fft=self.n_fft, win_length=self.win_length, hop_length=self.hop_length,
             window=window if window in ("hann", "hamming", "blackman", "bartlett") else "none",
             n_mels=nfilt, lowfreq=lowfreq, highfreq=highfreq or sample_rate / 2, mel_norm=mel_norm,
-            spec_floor=0.0, mag_power=mag_power, log_mode=(log_zero_guard_type if log else None),
+            spec_floor=CONSTANT if use_grads else 0.0, mag_power=mag_power, log_mode=(log_zero_guard_type if log else None),
             log_guard=guard, exact_pad=exact_pad, preemph=preemph,
             normalize=normalize if normalize in ("per_feature", "all_features") else None,
             pad_value=pad_value, pad_to=int(pad_to) if pad_to else 0,
@@ -136,23 +139,8 @@ class FilterbankFeatures(nn.Module):
         except Exception:
             pass
 
-    @torch.no_grad()
-    def forward(self, x, seq_len, linear_spec=False):
-        if linear_spec:
-            raise NotImplementedError("linear_spec=True is outside the accelerated path")
-        if self.training and (self.dither > 0 or self.nb_augmentation_prob > 0.0):
-            raise NotImplementedError("training-time dither / narrow-band augmentation are outside the accelerated "
-                                      "path: call .eval() or construct with dither=0.0")
-        if not x.is_cuda:
-            raise _lib.RoarSupError("roar_b200.FilterbankFeatures needs CUDA tensors (no CPU fallback)")
-        x = x.contiguous().float()
+    def _run_forward(self, x, lens):
         B, Lmax = x.shape
-        lens = seq_len.to(device=x.device, dtype=torch.int64).contiguous()
-        if self.normalize == "per_feature" and bool((self.get_seq_len(lens) == 1).any()):
-            raise ValueError(
-                "normalize_batch with `per_feature` normalize_type received a tensor of length 1. This will result "
-                "in torch.std() returning nan. Make sure your audio length has enough samples for a single "
-                "feature (ex. at least `hop_length` for Mel Spectrograms).")
         h = self._handle(x.device)
         Tpad = int(self._lib.roar_fbank_out_frames(h, Lmax))
         out = torch.empty(B, self.nfilt, Tpad, dtype=torch.float32, device=x.device)
@@ -164,6 +152,54 @@ class FilterbankFeatures(nn.Module):
             h, _ptr(x), _ptr(lens), B, Lmax, _ptr(out), _ptr(out_len), _ptr(self._ws), self._ws.numel(),
             ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
         return out, out_len
+
+    def _run_backward(self, x, lens, grad_out):
+        B, Lmax = x.shape
+        h = self._handle(x.device)
+        gx = torch.empty_like(x)
+        _lib.check(self._lib.roar_fbank_backward(
+            h, _ptr(x), _ptr(lens), B, Lmax, _ptr(grad_out.contiguous().float()), _ptr(gx), _ptr(self._ws),
+            self._ws.numel(), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+        return gx
+
+    def forward(self, x, seq_len, linear_spec=False):
+        if linear_spec:
+            raise NotImplementedError("linear_spec=True is outside the accelerated path")
+        if self.training and (self.dither > 0 or self.nb_augmentation_prob > 0.0):
+            raise NotImplementedError("training-time dither / narrow-band augmentation are outside the accelerated "
+                                      "path: call .eval() or construct with dither=0.0")
+        if not x.is_cuda:
+            raise _lib.RoarSupError("roar_b200.FilterbankFeatures needs CUDA tensors (no CPU fallback)")
+        lens = seq_len.to(device=x.device, dtype=torch.int64).contiguous()
+        if self.normalize == "per_feature" and bool((self.get_seq_len(lens) == 1).any()):
+            raise ValueError(
+                "normalize_batch with `per_feature` normalize_type received a tensor of length 1. This will result "
+                "in torch.std() returning nan. Make sure your audio length has enough samples for a single "
+                "feature (ex. at least `hop_length` for Mel Spectrograms).")
+        if self.use_grads and torch.is_grad_enabled() and x.requires_grad:
+            out, out_len = _FbankFunction.apply(x, lens, self)
+            return out, out_len
+        with torch.no_grad():
+            return self._run_forward(x.contiguous().float(), lens)
+
+
+class _FbankFunction(torch.autograd.Function):
+    """autograd through the CUDA preprocessor: forward = roar_fbank_forward, backward = roar_fbank_backward
+    (the forward spectrum is recomputed in the backward kernel, nothing but the audio is saved)."""
+
+    @staticmethod
+    def forward(ctx, x, lens, module):
+        xc = x.contiguous().float()
+        out, out_len = module._run_forward(xc, lens)
+        ctx.save_for_backward(xc, lens)
+        ctx.module = module
+        ctx.mark_non_differentiable(out_len)
+        return out, out_len
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_len):
+        xc, lens = ctx.saved_tensors
+        return ctx.module._run_backward(xc, lens, grad_out), None, None
 
 
 class AudioToMelSpectrogramPreprocessor(nn.Module):
@@ -198,7 +234,6 @@ class AudioToMelSpectrogramPreprocessor(nn.Module):
             nb_augmentation_prob=nb_augmentation_prob, nb_max_freq=nb_max_freq, mel_norm=mel_norm,
             stft_exact_pad=stft_exact_pad, stft_conv=stft_conv)
 
-    @torch.no_grad()
     def forward(self, *, input_signal, length):
         return self.get_features(input_signal, length)
 

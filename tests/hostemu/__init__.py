@@ -82,3 +82,15 @@ def trim(audio, top_db=60.0, ref_value=0.0, frame_length=2048, hop_length=512):
                         out.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0
     return int(out[0]), int(out[1])
+
+
+def fbank_backward(cfg, x, length, grad_out):
+    c = cfg.to_c()
+    x = _f32(x)
+    go = _f32(grad_out)
+    gx = np.zeros(len(x), np.float32)
+    rc = lib().emu_fbank_backward(ctypes.byref(c), x.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(x)),
+                                  ctypes.c_int64(int(length)), go.ctypes.data_as(ctypes.c_void_p),
+                                  gx.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return gx

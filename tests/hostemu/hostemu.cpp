@@ -14,6 +14,7 @@
 #include "../../roar_b200/csrc/fft.cuh"
 #include "../../roar_b200/csrc/tables.hpp"
 #include "../../roar_b200/csrc/k_stft_mel.cuh"
+#include "../../roar_b200/csrc/k_stft_bwd.cuh"
 #include "../../roar_b200/csrc/k_pyin_front.cuh"
 #include "../../roar_b200/csrc/k_viterbi.cuh"
 #include "../../roar_b200/csrc/k_misc.cuh"
@@ -278,6 +279,84 @@ int emu_prior(int32_t N, int32_t M, double scaling, float* out) {
   for (int m = 0; m < M; ++m)
     for (int k = 0; k < N; ++k)
       out[(size_t)m * N + k] = scaling == 1.0 ? prior_value_int(p, N, M, m + 1, k) : prior_value_real(p, N, M, m + 1, k);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- K1b backward (one utterance, dense)
+// x [Lmax] with `len` valid samples; grad_out [n_mels, T] (T = frames of Lmax); grad_x [Lmax]
+int emu_fbank_backward(const roar_sup_config* cfg, const float* x, int64_t Lmax, int64_t len, const float* grad_out,
+                       float* grad_x) {
+  if (!validate(*cfg).empty()) return -1;
+  Geometry g = geometry(*cfg);
+  std::vector<float> win = make_window(*cfg);
+  std::vector<float> fb = make_mel_filterbank(*cfg);
+  MelRows mr = make_mel_rows(fb, g.n_mels, g.n_bins);
+  std::vector<cf32> tw = make_pass_twiddles<cf32, float>(g.M);
+  std::vector<cf32> twp = make_twiddles<cf32, float>(g.n_fft, g.M + 1);
+  const int NT = 256;
+  StftBwdParams q;
+  memset(&q, 0, sizeof(q));
+  StftParams& p = q.f;
+  p.n_fft = g.n_fft; p.hop = g.hop; p.M = g.M; p.n_bins = g.n_bins; p.n_mels = g.n_mels;
+  p.P = g.M / 8; p.G = NT / p.P < 1 ? 1 : NT / p.P;
+  p.FT = g.n_fft <= 1024 ? 16 : 8; if (p.FT < p.G) p.FT = p.G;
+  p.span = (p.FT - 1) * g.hop + g.n_fft;
+  p.pad_left = cfg->exact_pad ? (g.n_fft - g.hop) / 2 : g.n_fft / 2;
+  p.floor_ = (float)cfg->spec_floor; p.mag_power = (float)cfg->mag_power; p.log_guard = (float)cfg->log_guard;
+  p.log_mode = cfg->log_mode; p.has_preemph = 0;
+  p.window = win.data(); p.tw = tw.data(); p.tw_post = twp.data();
+  p.mel_start = mr.start.data(); p.mel_count = mr.count.data(); p.mel_offset = mr.offset.data();
+  p.mel_w = mr.weights.data(); p.mel_nw = (int)mr.weights.size();
+  const int64_t T = cfg->exact_pad ? (Lmax + 2 * p.pad_left - g.n_fft) / g.hop + 1 : 1 + Lmax / g.hop;
+  int64_t num = len + 2 * p.pad_left - g.n_fft;
+  int64_t valid[1] = {(num >= 0 ? num / g.hop : -((-num + g.hop - 1) / g.hop)) + 1};
+  int64_t sample_off[1] = {0}; int32_t sample_len[1] = {(int32_t)Lmax};
+  int64_t frame_off[2] = {0, T};
+  int32_t n_tiles = (int32_t)((T + p.FT - 1) / p.FT);
+  int32_t tile_off[2] = {0, n_tiles};
+  p.audio = x; p.sample_off = sample_off; p.sample_len = sample_len; p.frame_off = frame_off;
+  p.tile_off = tile_off; p.n_utts = 1;
+  p.out_utt_stride = (int64_t)g.n_mels * T; p.out_row_stride = T;
+  q.grad_out = grad_out; q.valid_len = valid; q.grad_audio = grad_x;
+  for (int64_t i = 0; i < Lmax; ++i) grad_x[i] = 0.f;
+  const size_t fwd_bytes = stft_smem_carve(p, NT, nullptr, nullptr);
+  std::vector<unsigned char> smem(fwd_bytes + stft_bwd_extra_carve(p, nullptr, nullptr) + 64);
+  const FftPlan plan = make_plan(p.M);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    StftSmem s;
+    stft_smem_carve(p, NT, smem.data(), &s);
+    StftBwdSmem b;
+    stft_bwd_extra_carve(p, smem.data() + fwd_bytes, &b);
+    StftTile t;
+    if (!stft_locate(p, tile, &t)) continue;
+    const int hi = (t.nf - 1) * p.hop + p.n_fft;
+    for (int tid = 0; tid < NT; ++tid) { stft_phase_tables(p, s, tid, NT); stft_phase_audio(p, t, s, tid, NT, 0, hi); }
+    for (int i = 0; i < p.span; ++i) b.gspan[i] = 0.f;
+    const int n_groups = (t.nf + p.G - 1) / p.G;
+    for (int gi = 0; gi < n_groups; ++gi) {
+      for (int tid = 0; tid < NT; ++tid) stft_first_pass<8>(p, t, s, gi, tid);
+      int Ns = plan.radix[0];
+      cf32* src = s.bufA; cf32* dst = s.bufB;
+      for (int ps = 1; ps < plan.n_pass; ++ps) {
+        for (int tid = 0; tid < NT; ++tid) stft_pass_any(plan.radix[ps], p, t, s, gi, tid, Ns, p.tw + plan.tw_off[ps], src, dst);
+        Ns *= plan.radix[ps];
+        cf32* tmp = src; src = dst; dst = tmp;
+      }
+      for (int tid = 0; tid < NT; ++tid) bwd_phase_spectrum(p, t, b, gi, tid, src, dst);
+      for (int tid = 0; tid < NT; ++tid) bwd_phase_mel(q, t, s, b, gi, tid, NT);
+      for (int tid = 0; tid < NT; ++tid) bwd_phase_gx(p, t, b, gi, tid, dst);
+      for (int tid = 0; tid < NT; ++tid) bwd_phase_pack(p, t, gi, tid, dst, src);
+      Ns = 1;
+      for (int ps = 0; ps < plan.n_pass; ++ps) {
+        for (int tid = 0; tid < NT; ++tid) bwd_pass_inv_any(plan.radix[ps], p, t, gi, tid, Ns, p.tw + plan.tw_off[ps], src, dst);
+        Ns *= plan.radix[ps];
+        cf32* tmp = src; src = dst; dst = tmp;
+      }
+      for (int slot = 0; slot < p.G; ++slot)
+        for (int tid = 0; tid < NT; ++tid) bwd_phase_accumulate(p, t, s, b, gi, slot, tid, NT, src);
+    }
+    for (int tid = 0; tid < NT; ++tid) bwd_phase_scatter(q, t, b, tid, NT);
+  }
   return 0;
 }
 

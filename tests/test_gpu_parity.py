@@ -583,3 +583,44 @@ def test_cli_with_trim(tmp_path, capsys):
         assert len(yt) < 22050 * 2 + 18000 and pitch.shape == (1 + len(yt) // 256,)
         of0, _, _ = opyin.pyin(yt, FMIN, FMAX, sr=22050, frame_length=1024, fill_na=0.0)
         assert np.array_equal(pitch, of0.astype(np.float32))
+
+
+def test_fbank_autograd_vs_torch():
+    """Row N4: FilterbankFeatures(use_grads=True) -- forward and d loss / d audio against torch autograd on
+    the CPU through the reference's statements (features.py:403-452), ragged batch with masked tails."""
+    from oracle import melfb
+    from roar_b200 import synth
+    from roar_b200.features import FilterbankFeatures
+    B, Lmax = 3, 22050
+    lens = np.array([22050, 15000, 9876])
+    x = np.zeros((B, Lmax), np.float32)
+    for i in range(B):
+        x[i, :lens[i]] = synth.synth_utterance(7, i, int(lens[i]), 22050, i)
+    m = FilterbankFeatures(sample_rate=22050, n_window_size=1024, n_window_stride=256, nfilt=80, n_fft=1024, lowfreq=0,
+                           highfreq=None, normalize=None, preemph=None, dither=0.0, log=True,
+                           log_zero_guard_type="clamp", log_zero_guard_value=1e-5, mag_power=1.0, pad_to=0,
+                           pad_value=-11.52, use_grads=True).cuda()
+    xg = torch.tensor(x, device="cuda", requires_grad=True)
+    out, out_len = m(xg, torch.tensor(lens, device="cuda"))
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    (out * go.cuda()).sum().backward()
+    # torch reference on the CPU
+    xt = torch.tensor(x, requires_grad=True)
+    win = torch.hann_window(1024, periodic=False)
+    X = torch.stft(xt, 1024, hop_length=256, win_length=1024, center=True, window=win, return_complex=True, pad_mode="reflect")
+    mag = torch.sqrt(torch.view_as_real(X).pow(2).sum(-1) + 1e-5)
+    fb = torch.tensor(melfb.mel_filterbank(22050, 1024, 80, 0.0, None))[None]
+    ref = torch.log(torch.clamp(torch.matmul(fb, mag), min=1e-5))
+    seq = torch.tensor((lens + 1024 - 1024) // 256 + 1)
+    mask = torch.arange(ref.shape[-1])[None, :] >= seq[:, None]
+    ref = ref.masked_fill(mask[:, None, :], -11.52)
+    (ref * go).sum().backward()
+    assert np.array_equal(out_len.cpu().numpy(), seq.numpy())
+    o = out.detach().cpu().numpy()
+    assert (np.abs(o - ref.detach().numpy()) / np.maximum(1, np.abs(ref.detach().numpy()))).max() <= 1e-4
+    g, gr = xg.grad.cpu().numpy(), xt.grad.numpy()
+    assert np.abs(g - gr).max() <= 1e-4 * np.abs(gr).max()
+    # no grad requested -> plain path, same values
+    with torch.no_grad():
+        o2, _ = m(torch.tensor(x, device="cuda"), torch.tensor(lens, device="cuda"))
+    assert torch.equal(o2, out.detach())

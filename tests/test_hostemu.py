@@ -204,3 +204,43 @@ def test_emu_trim_equals_oracle():
         assert hostemu.trim(y, 40, 0.5, 1024, 256) == se
     z = np.zeros(5000, np.float32)
     assert hostemu.trim(z) == otrim.trim(z)[1] == (0, 5000)
+
+
+def _torch_fbank_grad(x, length, go, n_fft=1024, hop=256, n_mels=80, guard=1e-5, log="clamp", lg=1e-5, power=1.0,
+                      pad_value=-11.52, sr=22050):
+    """torch autograd through the reference statements of FilterbankFeatures.forward with use_grads=True
+    (features.py:403-452): stft, sqrt(re^2 + im^2 + 1e-5), pow, fb @, log, mask."""
+    import torch
+    from oracle import melfb
+    xt = torch.tensor(x, dtype=torch.float32, requires_grad=True)
+    win = torch.hann_window(n_fft, periodic=False)
+    X = torch.stft(xt[None], n_fft, hop_length=hop, win_length=n_fft, center=True, window=win, return_complex=True,
+                   pad_mode="reflect")
+    mag = torch.sqrt(torch.view_as_real(X).pow(2).sum(-1) + guard)
+    if power != 1.0:
+        mag = mag.pow(power)
+    fb = torch.tensor(melfb.mel_filterbank(sr, n_fft, n_mels, 0.0, None))[None]
+    mel = torch.matmul(fb, mag)
+    out = torch.log(torch.clamp(mel, min=lg)) if log == "clamp" else torch.log(mel + lg)
+    seq = (length + 2 * (n_fft // 2) - n_fft) // hop + 1
+    out = out.masked_fill((torch.arange(out.shape[-1]) >= seq)[None, None], pad_value)
+    (out * torch.tensor(go)[None]).sum().backward()
+    return xt.grad.numpy()
+
+
+@pytest.mark.parametrize("length,kw,tkw", [
+    (9000, {}, {}),
+    (6000, {}, {}),                                                              # masked tail frames
+    (9000, dict(log_mode="add", log_guard=1.0), dict(log="add", lg=1.0)),
+    (9000, dict(mag_power=2.0), dict(power=2.0)),
+])
+def test_emu_fbank_backward_matches_torch_autograd(length, kw, tkw):
+    """K1b: d loss / d audio through the preprocessor (use_grads=True) against torch autograd."""
+    rng = np.random.default_rng(0)
+    x = _wav(3, 9000)
+    go = rng.standard_normal((80, 1 + len(x) // 256)).astype(np.float32)
+    cfg = SupConfig(highfreq=None, spec_floor=1e-5, log_mode=kw.get("log_mode", "clamp"),
+                    log_guard=kw.get("log_guard", 1e-5), mag_power=kw.get("mag_power", 1.0))
+    ref = _torch_fbank_grad(x, length, go, **tkw)
+    got = hostemu.fbank_backward(cfg, x, length, go)
+    assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()
