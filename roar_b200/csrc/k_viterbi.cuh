@@ -337,13 +337,16 @@ HD double vit3_lower_bound(const Vit3Step& c, const uint16_t* row_id, double lp_
   const cf64* row = c.lt2 + (int)row_id[ks] * VIT_TW;
   double lb = VIT_NEG;
   if (lane == 0) { const cf64 e = row[VIT_HW]; lb = lp_u + (c.vmax + (kv ? e.y : e.x)); }
-  for (int q = lane; q < nc; q += nl) {
+  // the first 32 candidates are enough for a lower bound (one per lane on the device: no loop)
+  const int ncl = nc < 32 ? nc : 32;
+  for (int q = lane; q < ncl; q += nl) {
     const int b = cbin[q];
     const int dd = b - ks + VIT_HW;
     double l = c.lt0;
     if ((unsigned)dd <= 2u * VIT_HW) { const cf64 e = row[dd]; l = kv ? e.x : e.y; }
     const double cand = clp[q] + (c.vmax + l);
     if (cand > lb) lb = cand;
+    if (nl == 32) break;
   }
   return lb;
 }
