@@ -25,10 +25,6 @@ template <> __device__ __forceinline__ cf32 ld_ro<cf32>(const cf32* p) {
   const float2 v = __ldg(reinterpret_cast<const float2*>(p));
   cf32 r; r.x = v.x; r.y = v.y; return r;
 }
-template <> __device__ __forceinline__ cf64 ld_ro<cf64>(const cf64* p) {
-  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
-  cf64 r; r.x = v.x; r.y = v.y; return r;
-}
 #endif
 
 template <bool INV, class C> HD void dft2(C* v) {

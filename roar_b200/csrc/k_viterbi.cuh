@@ -43,9 +43,6 @@ struct VitParams {
   double lt_max;                // largest banded table entry
 };
 
-struct VitBest { double v; int k; };
-HD bool vit_better(double v, int k, const VitBest& b) { return v > b.v || (v == b.v && k < b.k); }
-
 // One DP step for pitch bin j.  V: previous values as (voiced, unvoiced) pairs; returns the new pair,
 // writes the two back-pointers.  (kstar, vmax) = first global argmax of the previous values.
 // `row_ofs[i]` = row_id[i] * tw (entry offset of source bin i's row in the banded table).
