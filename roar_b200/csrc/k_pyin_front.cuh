@@ -122,6 +122,7 @@ HD bool pyin_locate(const PyinParams& p, int tile, PyinTile* t) {
 
 HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int tid, int nthr) {
   // energy terms first: asynchronous 4-byte copies on the device, consumed after the autocorrelation
+  // (consecutive threads take consecutive frames of one lag: the global reads stay sector-coalesced)
   const float* Eg = p.energy + (p.frame_off[t.utt] + t.t0);
   const int ne = (p.max_period + 1) * t.nf;
   for (int i = tid; i < ne; i += nthr) {
@@ -138,9 +139,31 @@ HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 #endif
-  for (int i = tid; i < p.ylen; i += nthr) {
+  // samples in groups of 4 (one padded group of the ypad layout = 4 doubles + 1 pad): a 16-byte load when
+  // the group lies inside the utterance and the source is aligned, scalar loads at the edges
+  const float* src = p.audio + t.off;
+  // (src + p0 + i) is 16-byte aligned for every i % 4 == 0 iff (address / 4 + p0) % 4 == 0
+  const bool aligned = (((reinterpret_cast<uintptr_t>(src) >> 2) + (uintptr_t)(t.p0 & 3)) & 3) == 0;
+  const int n4 = p.ylen >> 2;      // ylen is a multiple of 4
+  for (int g4 = tid; g4 < n4; g4 += nthr) {
+    const int i = g4 << 2;
     const int64_t q = t.p0 + i;
-    s.yd[ypad(i)] = (q >= 0 && q < t.L) ? (double)p.audio[t.off + q] : 0.0;
+    double* dst = s.yd + ypad(i);
+    float v0, v1, v2, v3;
+    if (aligned && q >= 0 && q + 3 < t.L) {
+#if defined(__CUDA_ARCH__)
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + q));
+      v0 = v.x; v1 = v.y; v2 = v.z; v3 = v.w;
+#else
+      v0 = src[q]; v1 = src[q + 1]; v2 = src[q + 2]; v3 = src[q + 3];
+#endif
+    } else {
+      v0 = (q >= 0 && q < t.L) ? src[q] : 0.f;
+      v1 = (q + 1 >= 0 && q + 1 < t.L) ? src[q + 1] : 0.f;
+      v2 = (q + 2 >= 0 && q + 2 < t.L) ? src[q + 2] : 0.f;
+      v3 = (q + 3 >= 0 && q + 3 < t.L) ? src[q + 3] : 0.f;
+    }
+    dst[0] = (double)v0; dst[1] = (double)v1; dst[2] = (double)v2; dst[3] = (double)v3;
   }
 }
 

@@ -6,6 +6,7 @@ Mirrors what ``TTSDataset.__getitem__`` computes per utterance
 for device memory and streams only; all arithmetic happens in the CUDA library.
 """
 import ctypes
+import os
 from contextlib import nullcontext as _nullcontext
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
@@ -280,7 +281,8 @@ class SupDataExtractor:
         # side runs on a second stream (its own workspace), forked from / joined to the caller's stream,
         # so its CTAs fill the SMs the latency-bound Viterbi leaves idle.
         main = torch.cuda.current_stream(self.device)
-        side = self._side_stream() if (want_pitch and want_spec and batch.n_utts > 0) else None
+        overlap = want_pitch and want_spec and batch.n_utts > 0 and os.environ.get("ROAR_SUP_NO_OVERLAP") != "1"
+        side = self._side_stream() if overlap else None
         if side is not None:
             side.wait_stream(main)
         if want_spec:
