@@ -33,6 +33,55 @@ def _oracle_c4(args):
                                       dense_viterbi=False)
 
 
+def _oracle_c2(args):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import pyin as opyin
+    from oracle import spec as ospec
+    from roar_b200 import synth
+    seed, utt_id, n, sr, spk, fb = args
+    y = synth.synth_utterance(seed, utt_id, n, sr, spk)
+    f0, vf, vp = opyin.pyin(y, 65.40639132514966, 2093.004522404789, sr=sr, frame_length=1024, fill_na=0.0)
+    lm = ospec.get_log_mel(y, fb).numpy()[0]
+    return f0.astype(np.float32), vf, vp.astype(np.float32), lm
+
+
+def config2_sample(n_utts=2000):
+    """First n utterances of the BASELINE config-2 manifest (the bench workload): exactness of the pYIN outputs
+    and the log-mel error over ~1e6 frames."""
+    import torch
+    from roar_b200 import synth
+    from roar_b200.config import SupConfig
+    from roar_b200.extractor import SupDataExtractor, split_frames
+    man = synth.corpus_manifest("C2", n_utts)
+    ex = SupDataExtractor(SupConfig(highfreq=8000.0))
+    fb = ex.mel_filterbank()
+    tasks = [(2, u.utt_id, u.n_samples, 22050, u.speaker, fb) for u in man]
+    t0 = time.time()
+    with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+        refs = pool.map(_oracle_c2, tasks, chunksize=4)
+    t_cpu = time.time() - t0
+    wavs = [synth.synth_utterance(*t[:5]) for t in tasks]
+    out = ex.extract(ex.pack(wavs), types=("log_mel", "pitch", "voiced_mask", "p_voiced"))
+    torch.cuda.synchronize()
+    fo = out["frame_off"]
+    lms = split_frames(out["log_mel"], fo, 80)
+    f0a, vfa, vpa = out["pitch"].cpu().numpy(), out["voiced_mask"].cpu().numpy(), out["p_voiced"].cpu().numpy()
+    frames = flag_bad = f0_bad = 0
+    worst_lm = worst_vp = 0.0
+    for i, (rf0, rvf, rvp, rlm) in enumerate(refs):
+        a, b = int(fo[i]), int(fo[i + 1])
+        frames += b - a
+        flag_bad += int((vfa[a:b] != rvf.astype(np.float32)).sum())
+        f0_bad += int((f0a[a:b] != rf0).sum())
+        worst_vp = max(worst_vp, float(np.abs(vpa[a:b] - rvp).max()))
+        worst_lm = max(worst_lm, float((np.abs(lms[i].cpu().numpy() - rlm) / np.maximum(1, np.abs(rlm))).max()))
+    return {"workload": f"C2: first {n_utts} utterances of the bench manifest ({frames} frames, "
+                        f"{sum(len(w) for w in wavs) / 22050 / 3600:.2f} h)",
+            "voiced_flag_mismatches": flag_bad, "f0_not_bit_equal": f0_bad, "p_voiced_max_abs_err": worst_vp,
+            "log_mel_max_rel_err": worst_lm, "oracle_cpu_seconds": t_cpu}
+
+
 def config4(n_utts=6):
     """BASELINE config 4: 44.1 kHz, n_fft 2048 / hop 512 / 80 mels, fmax None, long utterances."""
     import torch
@@ -165,6 +214,7 @@ def main():
           and rep["f0_within_1_cent_frac_of_voiced"] >= 0.999 and rep["prior_argmax_exact_frac"] >= 0.999
           and rep["pitch_mean_rel_err"] <= 1e-5 and rep["pitch_std_rel_err"] <= 1e-5)
     rep["all_gates_pass"] = bool(ok)
+    rep["config2_sample"] = config2_sample()
     rep["config4"] = config4()
     rep["config5"] = config5()
     os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
