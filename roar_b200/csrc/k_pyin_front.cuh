@@ -602,8 +602,18 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
   for (int64_t frame = (int64_t)blockIdx.x * wpb + warp; frame < p.total_frames;
        frame += (int64_t)gridDim.x * wpb) {
     prob_phase0(p, s, frame, lane); __syncwarp();
-    prob_phase1(p, s, lane); __syncwarp();
-    prob_phase2(p, s, lane); __syncwarp();
+    {   // troughs in lag order: lane-strided test + ballot compaction (same list as prob_phase1/2)
+      int base = 0;
+      for (int i0 = 0; i0 < p.n_lags; i0 += 32) {
+        const int i = i0 + lane;
+        const bool tr = i < p.n_lags && prob_is_trough(s.x, i, p.n_lags);
+        const unsigned m = __ballot_sync(0xffffffffu, tr);
+        if (tr) s.tr[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        base += __popc(m);
+      }
+      if (lane == 0) s.cnt[32] = base;
+    }
+    __syncwarp();
     prob_phase3(p, s, lane, thr); __syncwarp();
     prob_phase4(p, s, lane); __syncwarp();
     {
@@ -641,15 +651,19 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
         const int r = a < na ? (int)s.sorted[a] : -1;
         const int cr = r >= 0 ? (int)s.cr[r] : 0x7fff;
         const bool more = base + 32 < na;
-        double acc = 0.0;
+        double acc = 0.0, K = 0.0;     // K = fact[n_c] * exp(-lambda * pos): changes only where a trough starts
         int pos = 0, n = 0;
         for (int c = cmin; c < p.n_thr; ++c) {
-          const unsigned m = __ballot_sync(0xffffffffu, cr == c);
-          const int cy = carry[c];
-          n += hist[c];
-          pos += cy + __popc(m & lt_mask);
-          if (c >= cr) acc += (bfact[n] * bexp[pos]) * beta[c];
-          if (more && lane == 0 && m) carry[c] = cy + __popc(m);
+          const int hc = hist[c];      // warp-uniform
+          if (hc) {
+            const unsigned m = __ballot_sync(0xffffffffu, cr == c);
+            const int cy = carry[c];
+            n += hc;
+            pos += cy + __popc(m & lt_mask);
+            if (more && lane == 0 && m) carry[c] = cy + __popc(m);
+            K = bfact[n] * bexp[pos];
+          }
+          if (c >= cr) acc += K * beta[c];
         }
         if (r >= 0) prob_trough_finish(p, s, r, acc);
         __syncwarp();
@@ -657,7 +671,33 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
     }
     __syncwarp();
     prob_phase6a(p, s, lane); __syncwarp();
-    prob_phase6b(p, s, frame, lane); __syncwarp();
+    {   // prob_phase6b with the logarithms spread over the lanes; the voiced-probability sum stays serial
+      const int R = s.cnt[32];
+      uint16_t* ob = p.cand_bin + (size_t)frame * p.kmax;
+      double* ol = p.cand_lp + (size_t)frame * p.kmax;
+      int n = 0;
+      for (int b0 = 0; b0 < R; b0 += 32) {
+        const int r = R - 1 - (b0 + lane);
+        const bool live = r >= 0 && s.live[r];
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (live) {
+          const int pos = n + __popc(m & ((1u << lane) - 1u));
+          ob[pos] = (uint16_t)s.bin[r];
+          ol[pos] = log(s.prob[r] + 2.2250738585072014e-308);
+        }
+        n += __popc(m);
+      }
+      if (lane == 0) {
+        double vp = 0.0;
+        for (int r = R - 1; r >= 0; --r) if (s.live[r]) vp += s.prob[r];
+        if (vp < 0.0) vp = 0.0;
+        if (vp > 1.0) vp = 1.0;
+        p.n_cand[frame] = n;
+        p.lp_unvoiced[frame] = log((1.0 - vp) / (double)p.npb + 2.2250738585072014e-308);
+        p.voiced_prob[frame] = (float)vp;
+      }
+    }
+    __syncwarp();
   }
 }
 #endif  // __CUDACC__
