@@ -19,7 +19,7 @@
 
 namespace roar {
 
-constexpr int ACF_R = 12;   // lags per thread (multiple of 4: keeps the padded smem offsets static)
+constexpr int ACF_R = 11;   // lags per thread (odd: a lane stride of 11 doubles is bank-conflict-free, 31 lanes cover 341 lags)
 
 struct PyinParams {
   const float* audio;
@@ -67,11 +67,9 @@ HD int cmnd_ylen(int FT, int F, int hop, int BL, int nb, int n_groups) {
   const int b = (FT + nb - 2) * hop + BL + n_groups * ACF_R + 1;
   return ((a > b ? a : b) + 3) & ~3;
 }
-// one pad double per 4: a lane stride of ACF_R = 12 samples becomes 15 doubles -> conflict-free
-HD int ypad(int i) { return i + (i >> 2); }
 
 struct CmndSmem {
-  double* yd;      // [ypad(ylen)]   tile samples as float64 (exact), zero outside the utterance
+  double* yd;      // [ylen]   tile samples as float64 (exact), zero outside the utterance
   double* Q;       // [FT+nb-1][QS]  block partial autocorrelations; then d[f][tau] in place
   float* E;        // [max_period+1][FT]  the tile's energy terms (from K2a-0's scratch)
   // aliases of yd, valid once the autocorrelation is done
@@ -86,7 +84,7 @@ constexpr int CMND_SLOTS = 8;   // frames scanned concurrently (one warp each)
 HD size_t cmnd_smem_carve(const PyinParams& p, unsigned char* base, CmndSmem* s) {
   size_t o = 0;
 #define CARVE(field, type, count) { if (s) s->field = (type*)(base + o); o = cmnd_align16(o + sizeof(type) * (size_t)(count)); }
-  size_t ny = (size_t)ypad(p.ylen) + 4;
+  size_t ny = (size_t)p.ylen + 4;
   const size_t alias = (size_t)CMND_SLOTS * (p.max_period + 1) + (size_t)CMND_SLOTS * 64;
   if (ny < alias) ny = alias;
   CARVE(yd, double, ny)
@@ -139,8 +137,8 @@ HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 #endif
-  // samples in groups of 4 (one padded group of the ypad layout = 4 doubles + 1 pad): a 16-byte load when
-  // the group lies inside the utterance and the source is aligned, scalar loads at the edges
+  // samples in groups of 4: a 16-byte load when the group lies inside the utterance and the source is
+  // aligned, scalar loads at the edges
   const float* src = p.audio + t.off;
   // (src + p0 + i) is 16-byte aligned for every i % 4 == 0 iff (address / 4 + p0) % 4 == 0
   const bool aligned = (((reinterpret_cast<uintptr_t>(src) >> 2) + (uintptr_t)(t.p0 & 3)) & 3) == 0;
@@ -148,7 +146,7 @@ HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
   for (int g4 = tid; g4 < n4; g4 += nthr) {
     const int i = g4 << 2;
     const int64_t q = t.p0 + i;
-    double* dst = s.yd + ypad(i);
+    double* dst = s.yd + i;
     float v0, v1, v2, v3;
     if (aligned && q >= 0 && q + 3 < t.L) {
 #if defined(__CUDA_ARCH__)
@@ -252,39 +250,39 @@ HD int cmnd_lpc(const PyinParams& p) { const int c = cmnd_cpb(p); return (p.n_gr
 
 // One autocorrelation unit: block m, lag group g ->  Q[m][tau] = sum_{j=1..BL} y[m*hop+j] * y[m*hop+j+tau]
 // for tau = g*R .. g*R+R-1.  The window y[j+tau0 .. j+tau0+R-1] lives in registers and slides by one
-// sample per step (static rotation: the loop is unrolled by R).  m*hop and g*R are multiples of 4,
-// so every padded shared-memory offset inside the unrolled body is a compile-time constant.
+// sample per step (static rotation: the loop is unrolled by R; every shared-memory offset inside the
+// unrolled body is a compile-time constant).
 HD void cmnd_acf_unit(const PyinParams& p, CmndSmem& s, int m, int g) {
   constexpr int R = ACF_R;
   const int b0 = m * p.hop;                // j = 1..BL -> samples b0+1 .. b0+BL
-  const double* ya = s.yd + ypad(b0);
-  const double* yw = s.yd + ypad(b0 + g * R);
+  const double* ya = s.yd + b0;
+  const double* yw = s.yd + b0 + g * R;
   double acc[R], win[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.0;
 #pragma unroll
-  for (int r = 0; r < R - 1; ++r) win[r] = yw[(r + 1) + ((r + 1) >> 2)];
+  for (int r = 0; r < R - 1; ++r) win[r] = yw[r + 1];
   const int full = p.BL / R * R;
   int jj = 0;
   for (; jj < full; jj += R) {
-    const double* a_ = ya + jj + (jj >> 2);
-    const double* w_ = yw + jj + (jj >> 2);
+    const double* a_ = ya + jj;
+    const double* w_ = yw + jj;
 #pragma unroll
     for (int st = 0; st < R; ++st) {
-      const double a = a_[(st + 1) + ((st + 1) >> 2)];
-      win[(st + R - 1) % R] = w_[(st + R) + ((st + R) >> 2)];
+      const double a = a_[st + 1];
+      win[(st + R - 1) % R] = w_[st + R];
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = fma(a, win[(st + r) % R], acc[r]);
     }
   }
   {   // tail (BL not a multiple of R): same body, guarded
-    const double* a_ = ya + jj + (jj >> 2);
-    const double* w_ = yw + jj + (jj >> 2);
+    const double* a_ = ya + jj;
+    const double* w_ = yw + jj;
 #pragma unroll
     for (int st = 0; st < R; ++st) {
       if (jj + st < p.BL) {
-        const double a = a_[(st + 1) + ((st + 1) >> 2)];
-        win[(st + R - 1) % R] = w_[(st + R) + ((st + R) >> 2)];
+        const double a = a_[st + 1];
+        win[(st + R - 1) % R] = w_[st + R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = fma(a, win[(st + r) % R], acc[r]);
       }
