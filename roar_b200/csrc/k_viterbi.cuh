@@ -203,8 +203,21 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
 //     Wc = fl(vvmax + lt_max) (vvmax = exact max over voiced V[t-1,.], lt_max = largest table entry).
 //     If the best offer so far (unvoiced band scan + out-of-band) is > Wc for both destination
 //     voicings, the voiced band scan is skipped (unvoiced stretches); otherwise it runs.
-// Both rules only skip sources that lose strictly, so values, back-pointers and the decoded path are
-// bit-identical to the dense recursion (checked against it in tests/).
+//   * IRRELEVANT voiced states.  Bin j is a candidate of frame t when K2b listed it (non-zero
+//     observation); every other voiced state has lp = lt0 = log(tiny).  Its value X = fl(lt0 + bv)
+//     sits far below its unvoiced twin X' = fl(lp_u + bu): the offers that built bv and bu come from
+//     the same sources through the (same, switch) pair of one table slot, so bv - bu <= ln 99, hence
+//     X - X' <= lt0 - lp_u + ln 99.  As sources at t+1 the two states again use one table slot, so the
+//     twin's offer is larger by >= lp_u - lt0 - 2 ln 99 for EVERY destination: strictly larger whenever
+//     lp_u >= lt0 + 16 (true unless voiced_prob clipped to exactly 1).  Such a voiced state never wins,
+//     never ties, is never the arg-max: its value and back-pointer cannot reach the decoded path.  In
+//     those ("sparse") steps the bin threads compute the unvoiced destination only (a band scan that
+//     reads one table component), the voiced row is filled with the sentinel, and the few candidate
+//     bins (4 per frame on average) are evaluated one per warp, lanes striding the sources.  Frames
+//     with lp_u < lt0 + 16 take the dense step (both voicings for every bin).
+// All rules only skip sources that lose strictly, so the decoded path is bit-identical to the dense
+// recursion (checked against it in tests/); values and back-pointers are identical for every state
+// that is not irrelevant in the sense above.
 //
 // The band scan is fully unrolled (51 sources): V rows are padded by hw sentinels (-1e308) on both
 // sides and a zero row is appended to the table for them, row ids of a thread's 51 sources are packed
@@ -324,6 +337,90 @@ HD void vit3_step_bin(const Vit3Step& c, int j, const uint32_t* rid, double lp_v
   *out_v = lp_v + bv.b; *out_u = lp_u + bu.b;
   *ptr_v = bv.a; *ptr_u = bu.a;
 }
+
+// light band scan: one table component (COMP 0 = same voicing, 1 = switch) -> one destination
+template <int COMP>
+HD void vit_band_scan1(const double* Vp, const cf64* lt2, const uint32_t* rid, double* best, int* best_d) {
+  double b = VIT_NEG;
+  int bd = 0;
+#pragma unroll
+  for (int d = 0; d < VIT_TW; ++d) {
+    const double v = Vp[d];
+    const uint32_t row = (rid[d / 5] >> (6 * (d % 5))) & 63u;
+    const double* e = reinterpret_cast<const double*>(lt2 + row * VIT_TW + (2 * VIT_HW - d));
+    const double s0 = v + e[COMP];
+    if (s0 > b) { b = s0; bd = d; }
+  }
+  *best = b; *best_d = bd;
+}
+
+HD void vit_list_offer1(const VitLive& e, int state_base, const cf64* lt2, int j, int comp, VitBest2& x) {
+  const int dd = j - e.kb + VIT_HW;
+  if ((unsigned)dd <= 2u * VIT_HW) {
+    const double* l = reinterpret_cast<const double*>(lt2 + e.row * VIT_TW + dd);
+    vit_offer(x, e.v + l[comp], state_base + e.kb);
+  }
+}
+
+// sparse step, bin thread: the unvoiced destination of pitch bin j
+HD void vit4_step_unvoiced(const Vit3Step& c, int j, const uint32_t* rid, double lp_u, double* out_u, int* ptr_u) {
+  VitBest2 bu;
+  bu.b = VIT_NEG; bu.a = 0x7fffffff;
+  {
+    const int ks = c.kstar >= c.npb ? c.kstar - c.npb : c.kstar;
+    const int dist = ks > j ? ks - j : j - ks;
+    if (dist > VIT_HW) vit_offer(bu, c.vmax + c.lt0, c.kstar);
+  }
+  if (c.nu > VIT_LIST_MAX) {
+    double sb; int sd;
+    vit_band_scan1<0>(c.Vu + j, c.lt2, rid, &sb, &sd);
+    vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
+  } else {
+    for (int e = 0; e < c.nu; ++e) vit_list_offer1(c.Lu[e], c.npb, c.lt2, j, 0, bu);
+  }
+  if (c.nv > VIT_LIST_MAX) {
+    const double Wc = c.vvmax + c.lt_max;
+    if (!(bu.b > Wc)) {
+      double wb; int wd;
+      vit_band_scan1<1>(c.Vv + j, c.lt2, rid, &wb, &wd);
+      vit_offer(bu, wb, j - VIT_HW + wd);
+    }
+  } else {
+    for (int e = 0; e < c.nv; ++e) vit_list_offer1(c.Lv[e], 0, c.lt2, j, 1, bu);
+  }
+  *out_u = lp_u + bu.b; *ptr_u = bu.a;
+}
+
+// sparse step, candidate bin b (voiced destination): this lane's share of the offers.  `lane`/`nl`
+// stride the sources (nl = 1 on the host); the caller reduces the partials to (max, smallest index).
+HD VitBest2 vit4_cand_partial(const Vit3Step& c, const uint16_t* row_id, int b, int lane, int nl) {
+  VitBest2 x;
+  x.b = VIT_NEG; x.a = 0x7fffffff;
+  if (lane == 0) {
+    const int ks = c.kstar >= c.npb ? c.kstar - c.npb : c.kstar;
+    const int dist = ks > b ? ks - b : b - ks;
+    if (dist > VIT_HW) vit_offer(x, c.vmax + c.lt0, c.kstar);
+  }
+  if (c.nu > VIT_LIST_MAX) {
+    for (int d = lane; d < VIT_TW; d += nl) {
+      const int k = b - VIT_HW + d;
+      if (k >= 0 && k < c.npb) vit_offer(x, c.Vu[VIT_HW + k] + c.lt2[(int)row_id[k] * VIT_TW + (2 * VIT_HW - d)].y, c.npb + k);
+    }
+  } else {
+    for (int e = lane; e < c.nu; e += nl) vit_list_offer1(c.Lu[e], c.npb, c.lt2, b, 1, x);
+  }
+  if (c.nv > VIT_LIST_MAX) {
+    for (int d = lane; d < VIT_TW; d += nl) {
+      const int k = b - VIT_HW + d;
+      if (k >= 0 && k < c.npb) vit_offer(x, c.Vv[VIT_HW + k] + c.lt2[(int)row_id[k] * VIT_TW + (2 * VIT_HW - d)].x, k);
+    }
+  } else {
+    for (int e = lane; e < c.nv; e += nl) vit_list_offer1(c.Lv[e], 0, c.lt2, b, 0, x);
+  }
+  return x;
+}
+// frames whose unvoiced observation is at least this far above log(tiny) take the sparse step
+constexpr double VIT_SPARSE_MARGIN = 16.0;
 
 // lower bound on vmax_t: the best one-step continuation of k*_{t-1} into the unvoiced state of its own
 // bin or into one of frame t's candidate bins.  `lane`/`nl` stride the candidate list (nl = 1 on the host).
@@ -495,7 +592,35 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     bestv = VIT_NEG; bestk = 0x7fffffff; vvb = VIT_NEG;
     bool live_v = false, live_u = false;
     double nv = VIT_NEG, nu = VIT_NEG;
-    if (j < npb) {
+    const bool sparse = lp_u >= p.lt0 + VIT_SPARSE_MARGIN;     // block-uniform
+    if (sparse) {
+      // candidate bins of this frame: one per warp, lanes stride the sources
+      for (int q = warp; q < nc_cur; q += nwarp) {
+        const int b = s.cbin[wp][q];
+        VitBest2 x = vit4_cand_partial(c, s.rowid, b, lane, 32);
+        vit_warp_argmax_neg(x.b, x.a);
+        if (lane == 0) {
+          const double cv = s.clp[wp][q] + x.b;
+          s.Vv[wp][VIT_HW + b] = cv;
+          pr[b] = (uint16_t)x.a;
+          if (cv > bestv || (cv == bestv && b < bestk)) { bestv = cv; bestk = b; }
+          if (cv >= thr) {
+            const int pos = atomicAdd(&s.cnt[wl][0], 1);
+            if (pos < VIT_LIST_MAX) { VitLive e; e.v = cv; e.kb = b; e.row = s.rowid[b]; s.Lv[wl][pos] = e; }
+          }
+        }
+      }
+      if (j < npb) {
+        int au;
+        vit4_step_unvoiced(c, j, rid, lp_u, &nu, &au);
+        if (s.lpv[wp][j] == p.lt0) s.Vv[wp][VIT_HW + j] = VIT_NEG; else s.lpv[wp][j] = p.lt0;
+        s.Vu[wp][VIT_HW + j] = nu;
+        pr[npb + j] = (uint16_t)au;
+        if (nu > bestv || (nu == bestv && npb + j < bestk)) { bestv = nu; bestk = npb + j; }
+        live_u = nu >= thr;
+      }
+      vvb = 0.0;     // no per-segment voiced maxima in a sparse step: an overflowing voiced list is scanned
+    } else if (j < npb) {
       int av, au;
       vit3_step_bin(c, j, rid, s.lpv[wp][j], lp_u, &nv, &nu, &av, &au);
       s.lpv[wp][j] = p.lt0;
@@ -506,7 +631,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       live_v = nv >= thr; live_u = nu >= thr;
     }
     const int myrow = j < npb ? (int)s.rowid[j] : 0;
-    vit3_append(live_v, nv, j, myrow, s.Lv[wl], &s.cnt[wl][0], lane);
+    if (!sparse) vit3_append(live_v, nv, j, myrow, s.Lv[wl], &s.cnt[wl][0], lane);
     vit3_append(live_u, nu, j, myrow, s.Lu[wl], &s.cnt[wl][1], lane);
     if (tid < nc_next) { s.lpv[wp ^ 1][nb_bin] = nb_lp; s.cbin[wp ^ 1][tid] = (uint16_t)nb_bin; s.clp[wp ^ 1][tid] = nb_lp; }
     nc_cur = nc_next;

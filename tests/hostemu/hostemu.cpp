@@ -166,6 +166,11 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     }
   }
   // ---- K3 (same per-bin step functions; the block reductions are plain scans here)
+  if (getenv("ROAR_EMU_VERBOSE")) {
+    long tot = 0, mx = 0, over = 0, over16=0; double mlp = 0;
+    for (int64_t t = 0; t < T; ++t) { tot += n_cand[t]; if (n_cand[t] > mx) mx = n_cand[t]; if (n_cand[t] > 32) ++over; if (n_cand[t] > 16) ++over16; if (lp_unv[t] < mlp) mlp = lp_unv[t]; }
+    fprintf(stderr, "cand: T %ld mean %.2f max %ld frames>32 %ld >16 %ld min lp_u %.3f\n", (long)T, (double)tot / T, mx, over, over16, mlp);
+  }
   VitParams v;
   memset(&v, 0, sizeof(v));
   v.npb = g.npb; v.tw = g.tw; v.hw = g.hw; v.kmax = g.kmax; v.n_rows = tb.n_rows;
@@ -203,7 +208,8 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     std::vector<uint32_t> rid((size_t)npb * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) vit_pack_rows(tb.row_id.data(), npb, tb.n_rows, j, rid.data() + (size_t)j * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) { Vv[VIT_HW + j] = V[j].x; Vu[VIT_HW + j] = V[j].y; }
-    long skipped = 0, listed = 0;
+    long skipped = 0, listed = 0, n_sparse = 0;
+    bool sparse_prev = false;
     for (int64_t t = 1; t < T; ++t) {
       const int rp = (int)((t - 1) & 1), wp = (int)(t & 1), rl = (int)((t - 1) % 3), wl = (int)(t % 3), zl = (int)((t + 1) % 3);
       Vit3Step c;
@@ -224,26 +230,54 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
                                          cand_lp.data() + (size_t)t * g.kmax, n_cand[t], 0, 1);
       const double thr = lb + tb.lt0;
       for (int q = 0; q < n_cand[t]; ++q) lpv[cand_bin[(size_t)t * g.kmax + q]] = cand_lp[(size_t)t * g.kmax + q];
+      const bool sparse = lp_unv[t] >= tb.lt0 + VIT_SPARSE_MARGIN;
+      if (sparse) {
+        ++n_sparse;
+        // candidate bins (one warp each on the device; here the "lanes" are reduced by vit_offer)
+        for (int q = 0; q < n_cand[t]; ++q) {
+          const int b = cand_bin[(size_t)t * g.kmax + q];
+          VitBest2 x; x.b = VIT_NEG; x.a = 0x7fffffff;
+          for (int lane = 0; lane < 32; ++lane) {
+            const VitBest2 y = vit4_cand_partial(c, tb.row_id.data(), b, lane, 32);
+            vit_offer(x, y.b, y.a);
+          }
+          const double cv = cand_lp[(size_t)t * g.kmax + q] + x.b;
+          Vv[(size_t)wp * VP + VIT_HW + b] = cv;
+          ptr[(size_t)t * 2 * npb + b] = (uint16_t)x.a;
+          if (cv >= thr) { if (cnt[wl][0] < VIT_LIST_MAX) { VitLive e; e.v = cv; e.kb = b; e.row = tb.row_id[b]; Lv[(size_t)wl * VIT_LIST_MAX + cnt[wl][0]] = e; } ++cnt[wl][0]; }
+        }
+        c.vvmax = 0.0;   // placeholder, replaced per bin below
+      }
       for (int j = 0; j < npb; ++j) {
         double nv, nu; int av, au;
-        {   // the kernel's per-warp bound: voiced maximum over the 32-bin segments w-1, w, w+1
+        if (sparse_prev) {
+          c.vvmax = 0.0;  // the kernel keeps no per-segment voiced maxima after a sparse step
+        } else {   // the kernel's per-warp bound: voiced maximum over the 32-bin segments w-1, w, w+1
           const int w = j / 32, nw = (npb + 31) / 32;
           double seg = -1e308;
           for (int ww = (w > 0 ? w - 1 : 0); ww <= (w + 1 < nw ? w + 1 : nw - 1); ++ww)
             for (int q = ww * 32; q < ww * 32 + 32 && q < npb; ++q) if (c.Vv[VIT_HW + q] > seg) seg = c.Vv[VIT_HW + q];
           c.vvmax = seg;
         }
-        vit3_step_bin(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lpv[j], lp_unv[t], &nv, &nu, &av, &au);
-        Vv[(size_t)wp * VP + VIT_HW + j] = nv; Vu[(size_t)wp * VP + VIT_HW + j] = nu;
-        ptr[(size_t)t * 2 * npb + j] = (uint16_t)av; ptr[(size_t)t * 2 * npb + npb + j] = (uint16_t)au;
-        if (nv >= thr) { if (cnt[wl][0] < VIT_LIST_MAX) { VitLive e; e.v = nv; e.kb = j; e.row = tb.row_id[j]; Lv[(size_t)wl * VIT_LIST_MAX + cnt[wl][0]] = e; } ++cnt[wl][0]; }
+        if (sparse) {
+          vit4_step_unvoiced(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lp_unv[t], &nu, &au);
+          if (lpv[j] == tb.lt0) Vv[(size_t)wp * VP + VIT_HW + j] = VIT_NEG;
+          Vu[(size_t)wp * VP + VIT_HW + j] = nu;
+          ptr[(size_t)t * 2 * npb + npb + j] = (uint16_t)au;
+        } else {
+          vit3_step_bin(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lpv[j], lp_unv[t], &nv, &nu, &av, &au);
+          Vv[(size_t)wp * VP + VIT_HW + j] = nv; Vu[(size_t)wp * VP + VIT_HW + j] = nu;
+          ptr[(size_t)t * 2 * npb + j] = (uint16_t)av; ptr[(size_t)t * 2 * npb + npb + j] = (uint16_t)au;
+          if (nv >= thr) { if (cnt[wl][0] < VIT_LIST_MAX) { VitLive e; e.v = nv; e.kb = j; e.row = tb.row_id[j]; Lv[(size_t)wl * VIT_LIST_MAX + cnt[wl][0]] = e; } ++cnt[wl][0]; }
+        }
         if (nu >= thr) { if (cnt[wl][1] < VIT_LIST_MAX) { VitLive e; e.v = nu; e.kb = j; e.row = tb.row_id[j]; Lu[(size_t)wl * VIT_LIST_MAX + cnt[wl][1]] = e; } ++cnt[wl][1]; }
       }
+      sparse_prev = sparse;
       for (int q = 0; q < n_cand[t]; ++q) lpv[cand_bin[(size_t)t * g.kmax + q]] = tb.lt0;
     }
     const int lp_ = (int)((T - 1) & 1);
     for (int j = 0; j < npb; ++j) { V[(size_t)lp_ * npb + j].x = Vv[(size_t)lp_ * VP + VIT_HW + j]; V[(size_t)lp_ * npb + j].y = Vu[(size_t)lp_ * VP + VIT_HW + j]; }
-    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps\n", listed, skipped);
+    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps, %ld sparse steps\n", listed, skipped, n_sparse);
   } else {
   for (int64_t t = 1; t < T; ++t) {
     const cf64* Vc = V.data() + (size_t)((t - 1) & 1) * npb;
