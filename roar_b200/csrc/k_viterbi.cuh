@@ -21,6 +21,9 @@
 
 namespace roar {
 
+constexpr int VIT_TW = 51;   // fast-path transition width (k_pyin_viterbi51)
+constexpr int VIT_HW = 25;
+
 struct VitParams {
   const int64_t* frame_off;     // [n_utts+1]
   const int32_t* order;         // [n_utts] utterances by decreasing length
@@ -41,6 +44,10 @@ struct VitParams {
   int32_t lt_in_smem;
   int32_t ptr_stride, ptr_uoff;   // back-pointer row layout: [voiced | unvoiced at ptr_uoff], row stride
   double lt_max;                // largest banded table entry
+  // same-voicing entries of the representative interior row: kernel-parameter (constant bank) operands
+  // of the uniform band scan, valid while vmax <= uniform_vmax (tables.hpp make_uniform_row)
+  double uniform_vmax;
+  double ltu[VIT_TW];
 };
 
 // One DP step for pitch bin j.  V: previous values as (voiced, unvoiced) pairs; returns the new pair,
@@ -223,8 +230,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
 // sides and a zero row is appended to the table for them, row ids of a thread's 51 sources are packed
 // 5 x 6 bit per register once per utterance, so one scan step is LDS.64 + bit-field + LDS.128 + 2 DADD
 // + 2 compare/select.
-constexpr int VIT_TW = 51;
-constexpr int VIT_HW = 25;
 constexpr int VIT_LIST_MAX = 32;
 constexpr int VIT_CHAINS = 1;
 constexpr int VIT_RID_REGS = (VIT_TW + 4) / 5;   // 11
@@ -354,6 +359,19 @@ HD void vit_band_scan1(const double* Vp, const cf64* lt2, const uint32_t* rid, d
   *best = b; *best_d = bd;
 }
 
+// the same scan for a warp whose 32 + 2 hw sources are all interior bins, while vmax <= uniform_vmax:
+// one table row for everybody -> `row` is a kernel parameter, its entries immediate constant operands
+HD void vit_band_scan1u(const double* Vp, const double* row, double* best, int* best_d) {
+  double b = VIT_NEG;
+  int bd = 0;
+#pragma unroll
+  for (int d = 0; d < VIT_TW; ++d) {
+    const double s0 = Vp[d] + row[2 * VIT_HW - d];
+    if (s0 > b) { b = s0; bd = d; }
+  }
+  *best = b; *best_d = bd;
+}
+
 HD void vit_list_offer1(const VitLive& e, int state_base, const cf64* lt2, int j, int comp, VitBest2& x) {
   const int dd = j - e.kb + VIT_HW;
   if ((unsigned)dd <= 2u * VIT_HW) {
@@ -363,7 +381,8 @@ HD void vit_list_offer1(const VitLive& e, int state_base, const cf64* lt2, int j
 }
 
 // sparse step, bin thread: the unvoiced destination of pitch bin j
-HD void vit4_step_unvoiced(const Vit3Step& c, int j, const uint32_t* rid, double lp_u, double* out_u, int* ptr_u) {
+HD void vit4_step_unvoiced(const Vit3Step& c, int j, const uint32_t* rid, double lp_u, const double* uniform_row,
+                           double* out_u, int* ptr_u) {
   VitBest2 bu;
   bu.b = VIT_NEG; bu.a = 0x7fffffff;
   {
@@ -373,7 +392,8 @@ HD void vit4_step_unvoiced(const Vit3Step& c, int j, const uint32_t* rid, double
   }
   if (c.nu > VIT_LIST_MAX) {
     double sb; int sd;
-    vit_band_scan1<0>(c.Vu + j, c.lt2, rid, &sb, &sd);
+    if (uniform_row) vit_band_scan1u(c.Vu + j, uniform_row, &sb, &sd);
+    else vit_band_scan1<0>(c.Vu + j, c.lt2, rid, &sb, &sd);
     vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
   } else {
     for (int e = 0; e < c.nu; ++e) vit_list_offer1(c.Lu[e], c.npb, c.lt2, j, 0, bu);
@@ -612,7 +632,9 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       }
       if (j < npb) {
         int au;
-        vit4_step_unvoiced(c, j, rid, lp_u, &nu, &au);
+        // warp-uniform: every source of this warp's 32 destinations is an interior bin
+        const bool uni = c.vmax <= p.uniform_vmax && 32 * warp >= 2 * VIT_HW && 32 * warp + 31 + 2 * VIT_HW <= npb - 1;
+        vit4_step_unvoiced(c, j, rid, lp_u, uni ? p.ltu : nullptr, &nu, &au);
         if (s.lpv[wp][j] == p.lt0) s.Vv[wp][VIT_HW + j] = VIT_NEG; else s.lpv[wp][j] = p.lt0;
         s.Vu[wp][VIT_HW + j] = nu;
         pr[npb + j] = (uint16_t)au;

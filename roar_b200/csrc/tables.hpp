@@ -234,6 +234,12 @@ struct PyinTables {
   int n_rows = 0;
   double lt0 = 0;                   // log(0 + tiny): every out-of-band transition
   double lt_max = 0;                // largest entry of lt_rows
+  // interior rows (source bins hw .. npb-1-hw) differ only by the rounding of the row sum (a last-place
+  // unit in a few entries).  fl(V + lt) does not see that difference once |V| >= 2^uniform_emin (see
+  // make_uniform_row): then every interior source may use `lt_uniform` (the same-voicing entries of one
+  // representative row), which the kernel reads as an immediate constant operand.
+  std::vector<double> lt_uniform;   // [tw]; empty when tw != the fast path's width or npb too small
+  double uniform_vmax = -1e308;     // the uniform row is valid while vmax <= uniform_vmax
   double li_voiced = 0, li_unvoiced = 0;  // log(p_init + tiny)
 };
 
@@ -260,6 +266,40 @@ inline std::vector<double> triangle_window(int width) {  // scipy.signal.windows
     for (int i = 0; i < (width + 1) / 2; ++i) { w[i] = 2.0 * (i + 1) / (width + 1.0); w[width - 1 - i] = w[i]; }
   }
   return w;
+}
+
+// fl(V + a) == fl(V + b) for EVERY double V with |V| >= 2^e (a, b < 0 much smaller in magnitude) iff
+// no multiple of 2^(e-53) lies in the closed interval [min(a,b), max(a,b)]: V is a multiple of its own
+// ulp u >= 2^(e-52); the sum rounds to the grid u (same binade: boundaries at odd multiples of u/2) or
+// 2u (next binade: boundaries at odd multiples of u), i.e. the decision boundaries, shifted by -V, are
+// multiples of u/2 >= 2^(e-53); coarser grids are subsets of finer ones, so the finest e decides.
+inline int uniform_min_exponent(double a, double b) {
+  if (a == b) return -1074;
+  const double lo = a < b ? a : b, hi = a < b ? b : a;
+  for (int e = 1; e < 1000; ++e) {
+    const double sl = std::ldexp(lo, 53 - e), sh = std::ldexp(hi, 53 - e);   // exact scalings
+    if (std::ceil(sl) > std::floor(sh)) return e;
+  }
+  return 1000;
+}
+
+inline void make_uniform_row(PyinTables& t, const Geometry& g) {
+  const int n = g.npb, tw = g.tw, hw = g.hw;
+  if (n < 4 * hw + 2) return;
+  const int base = t.row_id[n / 2];
+  int emin = -1074;
+  for (int i = hw; i <= n - 1 - hw; ++i) {
+    const int r = t.row_id[i];
+    if (r == base) continue;
+    for (int d = 0; d < tw; ++d) {
+      const int e = uniform_min_exponent(t.lt_rows[((size_t)base * tw + d) * 2], t.lt_rows[((size_t)r * tw + d) * 2]);
+      if (e > emin) emin = e;
+    }
+  }
+  if (emin >= 1000) return;
+  t.lt_uniform.resize(tw);
+  for (int d = 0; d < tw; ++d) t.lt_uniform[d] = t.lt_rows[((size_t)base * tw + d) * 2];
+  t.uniform_vmax = emin <= -1074 ? 0.0 : -std::ldexp(1.0, emin);
 }
 
 inline PyinTables make_pyin_tables(const roar_sup_config& c, const Geometry& g) {
@@ -343,6 +383,7 @@ inline PyinTables make_pyin_tables(const roar_sup_config& c, const Geometry& g) 
   for (double v : t.lt_rows) if (v > t.lt_max) t.lt_max = v;
   t.li_voiced = std::log(0.0 + kTiny64);
   t.li_unvoiced = std::log(1.0 / n + kTiny64);
+  make_uniform_row(t, g);
   return t;
 }
 

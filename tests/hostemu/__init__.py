@@ -74,6 +74,13 @@ def prior_interp(text_len, mel_len, round_mel=50, round_text=10):
     return out
 
 
+def uniform_row_check(cfg, n_rand=64):
+    c = cfg.to_c()
+    out = np.zeros(4, np.float64)
+    rc = lib().emu_uniform_row_check(ctypes.byref(c), ctypes.c_int32(n_rand), out.ctypes.data_as(ctypes.c_void_p))
+    return rc, out
+
+
 def trim(audio, top_db=60.0, ref_value=0.0, frame_length=2048, hop_length=512):
     audio = _f32(audio)
     out = np.zeros(2, np.int64)

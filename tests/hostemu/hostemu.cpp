@@ -208,7 +208,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     std::vector<uint32_t> rid((size_t)npb * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) vit_pack_rows(tb.row_id.data(), npb, tb.n_rows, j, rid.data() + (size_t)j * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) { Vv[VIT_HW + j] = V[j].x; Vu[VIT_HW + j] = V[j].y; }
-    long skipped = 0, listed = 0, n_sparse = 0;
+    long skipped = 0, listed = 0, n_sparse = 0, n_uniform = 0;
     bool sparse_prev = false;
     for (int64_t t = 1; t < T; ++t) {
       const int rp = (int)((t - 1) & 1), wp = (int)(t & 1), rl = (int)((t - 1) % 3), wl = (int)(t % 3), zl = (int)((t + 1) % 3);
@@ -260,7 +260,11 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
           c.vvmax = seg;
         }
         if (sparse) {
-          vit4_step_unvoiced(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lp_unv[t], &nu, &au);
+          const int w = j / 32;
+          const bool uni = (int)tb.lt_uniform.size() == VIT_TW && c.vmax <= tb.uniform_vmax && 32 * w >= 2 * VIT_HW &&
+                           32 * w + 31 + 2 * VIT_HW <= npb - 1;
+          if (uni) ++n_uniform;
+          vit4_step_unvoiced(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lp_unv[t], uni ? tb.lt_uniform.data() : nullptr, &nu, &au);
           if (lpv[j] == tb.lt0) Vv[(size_t)wp * VP + VIT_HW + j] = VIT_NEG;
           Vu[(size_t)wp * VP + VIT_HW + j] = nu;
           ptr[(size_t)t * 2 * npb + npb + j] = (uint16_t)au;
@@ -277,7 +281,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     }
     const int lp_ = (int)((T - 1) & 1);
     for (int j = 0; j < npb; ++j) { V[(size_t)lp_ * npb + j].x = Vv[(size_t)lp_ * VP + VIT_HW + j]; V[(size_t)lp_ * npb + j].y = Vu[(size_t)lp_ * VP + VIT_HW + j]; }
-    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps, %ld sparse steps\n", listed, skipped, n_sparse);
+    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps, %ld sparse steps, %ld uniform bin-steps (uniform_vmax %g)\n", listed, skipped, n_sparse, n_uniform, tb.uniform_vmax);
   } else {
   for (int64_t t = 1; t < T; ++t) {
     const cf64* Vc = V.data() + (size_t)((t - 1) & 1) * npb;
@@ -304,6 +308,49 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
 }
 
 // ---------------------------------------------------------------------------- K4
+// Brute-force check of tables.hpp make_uniform_row: for every interior source row, every band offset
+// and `n_rand` doubles V <= uniform_vmax per binade (random mantissas plus the binade's corner cases),
+// fl(V + lt_row) must equal fl(V + lt_uniform).
+// out[0] = mismatches, out[1] = differing table entries, out[2] = -uniform_vmax, out[3] = sums compared.
+int emu_uniform_row_check(const roar_sup_config* cfg, int32_t n_rand, double* out) {
+  if (!validate(*cfg).empty()) return -1;
+  Geometry g = geometry(*cfg);
+  PyinTables tb = make_pyin_tables(*cfg, g);
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if ((int)tb.lt_uniform.size() != g.tw) return 1;
+  out[2] = -tb.uniform_vmax;
+  uint64_t rs = 0x9e3779b97f4a7c15ull;
+  auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return rs; };
+  long bad = 0, differing = 0, compared = 0;
+  for (int i = g.hw; i <= g.npb - 1 - g.hw; ++i) {
+    const int r = tb.row_id[i];
+    for (int d = 0; d < g.tw; ++d) {
+      const double a = tb.lt_rows[((size_t)r * g.tw + d) * 2], b = tb.lt_uniform[d];
+      if (a == b) continue;
+      ++differing;
+      int e0; std::frexp(tb.uniform_vmax == 0.0 ? -1.0 : tb.uniform_vmax, &e0);   // |vmax| = 2^(e0-1)
+      for (int e = e0 - 1; e < 40; ++e) {
+        const double u = std::ldexp(1.0, e - 52);
+        for (int k = 0; k < n_rand; ++k) {
+          // random mantissa, plus the structural cases: even / odd multiple of u at the bottom of the
+          // binade (sum stays inside) and at its top (sum crosses into the next binade)
+          double V = -std::ldexp(1.0 + (double)(rnd() >> 12) * std::ldexp(1.0, -52), e);
+          if (k == 0) V = -std::ldexp(1.0, e);
+          if (k == 1) V = -(std::ldexp(1.0, e) + u);
+          if (k == 2) V = -(std::ldexp(1.0, e + 1) - u);
+          if (k == 3) V = -(std::ldexp(1.0, e + 1) - 2 * u);
+          if (V > tb.uniform_vmax) continue;
+          volatile double s1 = V + a, s2 = V + b;
+          ++compared;
+          if (s1 != s2) ++bad;
+        }
+      }
+    }
+  }
+  out[0] = (double)bad; out[1] = (double)differing; out[3] = (double)compared;
+  return 0;
+}
+
 int emu_prior(int32_t N, int32_t M, double scaling, float* out) {
   std::vector<double> lf(4096);
   for (size_t i = 0; i < lf.size(); ++i) lf[i] = std::lgamma((double)i + 1.0);

@@ -124,6 +124,19 @@ def test_emu_viterbi_fast_path_equals_generic(monkeypatch):
         assert np.array_equal(fast[0], gen[0]) and np.array_equal(fast[1], gen[1])
 
 
+def test_uniform_interior_row_is_exact():
+    """Interior transition rows differ by a last-place unit in a few entries (rounding of the row sum);
+    the kernel's uniform band scan uses ONE row for all of them once vmax <= uniform_vmax.  Brute force:
+    the float64 sums are identical for every interior row, band offset and binade below that bound."""
+    for cfg in (SupConfig(highfreq=8000.0), SupConfig(sample_rate=44100, n_fft=2048, hop_length=512)):
+        rc, out = hostemu.uniform_row_check(cfg, 64)
+        assert rc == 0
+        mismatches, differing, bound, compared = out
+        assert differing > 0 and compared > 1000      # the premise: rows do differ
+        assert mismatches == 0
+        assert 1.0 <= bound <= 2.0 ** 14               # valid after a handful of frames
+
+
 def test_emu_prior(golden_dir):
     g = np.load(os.path.join(golden_dir, "prior_ref.npz"))
     for k in ("p_7_13", "p_100_560", "p_1_4", "p_2_9"):
