@@ -380,16 +380,13 @@ HD void vit_list_offer1(const VitLive& e, int state_base, const cf64* lt2, int j
   }
 }
 
-// sparse step, bin thread: the unvoiced destination of pitch bin j
-HD void vit4_step_unvoiced(const Vit3Step& c, int j, const uint32_t* rid, double lp_u, const double* uniform_row,
-                           double* out_u, int* ptr_u) {
+// sparse step, bin thread: the unvoiced destination of pitch bin j.  Part A visits the in-band sources
+// (it needs nothing but the previous rows and lists, so it runs while one warp still reduces the global
+// arg-max); part B adds the out-of-band offer of k*.  vit_offer breaks ties by state index, so the
+// order in which offers arrive does not matter.
+HD VitBest2 vit4_unvoiced_scan(const Vit3Step& c, int j, const uint32_t* rid, const double* uniform_row) {
   VitBest2 bu;
   bu.b = VIT_NEG; bu.a = 0x7fffffff;
-  {
-    const int ks = c.kstar >= c.npb ? c.kstar - c.npb : c.kstar;
-    const int dist = ks > j ? ks - j : j - ks;
-    if (dist > VIT_HW) vit_offer(bu, c.vmax + c.lt0, c.kstar);
-  }
   if (c.nu > VIT_LIST_MAX) {
     double sb; int sd;
     if (uniform_row) vit_band_scan1u(c.Vu + j, uniform_row, &sb, &sd);
@@ -408,6 +405,12 @@ HD void vit4_step_unvoiced(const Vit3Step& c, int j, const uint32_t* rid, double
   } else {
     for (int e = 0; e < c.nv; ++e) vit_list_offer1(c.Lv[e], 0, c.lt2, j, 1, bu);
   }
+  return bu;
+}
+HD void vit4_unvoiced_finish(VitBest2 bu, int npb, double lt0, double vmax, int kstar, int j, double lp_u, double* out_u, int* ptr_u) {
+  const int ks = kstar >= npb ? kstar - npb : kstar;
+  const int dist = ks > j ? ks - j : j - ks;
+  if (dist > VIT_HW) vit_offer(bu, vmax + lt0, kstar);
   *out_u = lp_u + bu.b; *ptr_u = bu.a;
 }
 
@@ -501,7 +504,8 @@ struct alignas(16) Vit3Shared {
   double wv[2][32], wvv[2][32];              // per-warp partials (= 32-bin segment stats)
   int wk[2][32];
   int cnt[3][2];
-  int pad_[2];
+  int pub_kstar, pad_;
+  double pub_vmax, pub_thr;                  // block-wide values of the running step (written by the lead warp)
   uint16_t cbin[2][VIT_KMAX_MAX];
   uint16_t rowid[VIT_NPB_MAX];
 };
@@ -570,34 +574,36 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
   if (lane == 0) { s.wv[0][warp] = bestv; s.wk[0][warp] = bestk; s.wvv[0][warp] = vvb; }
   __syncthreads();
 
+  // One warp (`lead`, an interior one) reduces the block-wide quantities of a step -- first global
+  // arg-max (k*, vmax), the lower bound and the liveness threshold -- and publishes them in shared
+  // memory; it signals named barrier 1 (bar.arrive) and the other warps wait on it (bar.sync) only
+  // after their in-band work, which does not depend on those values.
+  const int lead = nwarp >> 1;
+  double prev_vmax = 0.0;                              // vmax is strictly decreasing in t
   uint16_t* pr = p.ptr + (size_t)(f0 + 1) * (2 * npb);
   for (int t = 1; t < T; ++t, pr += 2 * npb) {
     const int rp = (t - 1) & 1, wp = t & 1;           // V / partial parity: read, write
     const int rl = (t - 1) % 3, wl = t % 3, zl = (t + 1) % 3;   // live-list slots: read, write, reset
     Vit3Step c;
-    {
-      double vmax = lane < nwarp ? s.wv[rp][lane] : VIT_NEG;
-      int kstar = lane < nwarp ? s.wk[rp][lane] : 0x7fffffff;
-      vit_warp_argmax_neg(vmax, kstar);
-      c.vmax = vmax; c.kstar = kstar;
-      // sources in band of this warp's destinations live in the 32-bin segments of warps w-1, w, w+1
-      double seg = s.wvv[rp][warp];
-      if (warp > 0) { const double x = s.wvv[rp][warp - 1]; if (x > seg) seg = x; }
-      if (warp + 1 < nwarp) { const double x = s.wvv[rp][warp + 1]; if (x > seg) seg = x; }
-      c.vvmax = seg;
-    }
     c.Vv = s.Vv[rp]; c.Vu = s.Vu[rp];
     c.Lv = s.Lv[rl]; c.Lu = s.Lu[rl];
     c.nv = s.cnt[rl][0]; c.nu = s.cnt[rl][1];
     c.lt2 = s.lt2; c.lt0 = p.lt0; c.lt_max = p.lt_max; c.npb = npb;
+    c.vmax = 0.0; c.kstar = 0; c.vvmax = 0.0;
     if (tid < 2) s.cnt[zl][tid] = 0;
     const double lp_u = lp_u_next;
-    // liveness threshold for the values this step produces
-    double thr;
-    {
+    double thr = 0.0;
+    if (warp == lead) {
+      double vmax = lane < nwarp ? s.wv[rp][lane] : VIT_NEG;
+      int kstar = lane < nwarp ? s.wk[rp][lane] : 0x7fffffff;
+      vit_warp_argmax_neg(vmax, kstar);
+      c.vmax = vmax; c.kstar = kstar;
+      // liveness threshold for the values this step produces
       double lb = vit3_lower_bound(c, s.rowid, lp_u, s.cbin[wp], s.clp[wp], nc_cur, lane, 32);
       lb = vit_warp_max(lb);
       thr = lb + p.lt0;
+      if (lane == 0) { s.pub_vmax = vmax; s.pub_thr = thr; s.pub_kstar = kstar; }
+      asm volatile("bar.arrive 1, %0;" ::"r"(nthr) : "memory");
     }
     // prefetch next frame's sparse observations (consumed after the band work)
     int nc_next = 0; unsigned nb_bin = 0; double nb_lp = 0.0;
@@ -614,6 +620,18 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     double nv = VIT_NEG, nu = VIT_NEG;
     const bool sparse = lp_u >= p.lt0 + VIT_SPARSE_MARGIN;     // block-uniform
     if (sparse) {
+      VitBest2 bu;
+      bu.b = VIT_NEG; bu.a = 0x7fffffff;
+      if (j < npb) {
+        if (c.nv > VIT_LIST_MAX) c.vvmax = 0.0;   // (after a dense step the segment maxima would do; rare)
+        // warp-uniform: every source of this warp's 32 destinations is an interior bin
+        const bool uni = prev_vmax <= p.uniform_vmax && 32 * warp >= 2 * VIT_HW && 32 * warp + 31 + 2 * VIT_HW <= npb - 1;
+        bu = vit4_unvoiced_scan(c, j, rid, uni ? p.ltu : nullptr);
+      }
+      if (warp != lead) {
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        c.vmax = s.pub_vmax; c.kstar = s.pub_kstar; thr = s.pub_thr;
+      }
       // candidate bins of this frame: one per warp, lanes stride the sources
       for (int q = warp; q < nc_cur; q += nwarp) {
         const int b = s.cbin[wp][q];
@@ -632,9 +650,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       }
       if (j < npb) {
         int au;
-        // warp-uniform: every source of this warp's 32 destinations is an interior bin
-        const bool uni = c.vmax <= p.uniform_vmax && 32 * warp >= 2 * VIT_HW && 32 * warp + 31 + 2 * VIT_HW <= npb - 1;
-        vit4_step_unvoiced(c, j, rid, lp_u, uni ? p.ltu : nullptr, &nu, &au);
+        vit4_unvoiced_finish(bu, npb, p.lt0, c.vmax, c.kstar, j, lp_u, &nu, &au);
         if (s.lpv[wp][j] == p.lt0) s.Vv[wp][VIT_HW + j] = VIT_NEG; else s.lpv[wp][j] = p.lt0;
         s.Vu[wp][VIT_HW + j] = nu;
         pr[npb + j] = (uint16_t)au;
@@ -642,16 +658,28 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
         live_u = nu >= thr;
       }
       vvb = 0.0;     // no per-segment voiced maxima in a sparse step: an overflowing voiced list is scanned
-    } else if (j < npb) {
-      int av, au;
-      vit3_step_bin(c, j, rid, s.lpv[wp][j], lp_u, &nv, &nu, &av, &au);
-      s.lpv[wp][j] = p.lt0;
-      s.Vv[wp][VIT_HW + j] = nv; s.Vu[wp][VIT_HW + j] = nu;
-      pr[j] = (uint16_t)av; pr[npb + j] = (uint16_t)au;
-      bestv = nv; bestk = j; vvb = nv;
-      if (nu > bestv) { bestv = nu; bestk = npb + j; }
-      live_v = nv >= thr; live_u = nu >= thr;
+    } else {
+      if (warp != lead) {
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        c.vmax = s.pub_vmax; c.kstar = s.pub_kstar; thr = s.pub_thr;
+      }
+      if (j < npb) {
+        // sources in band of this warp's destinations live in the 32-bin segments of warps w-1, w, w+1
+        double seg = s.wvv[rp][warp];
+        if (warp > 0) { const double x = s.wvv[rp][warp - 1]; if (x > seg) seg = x; }
+        if (warp + 1 < nwarp) { const double x = s.wvv[rp][warp + 1]; if (x > seg) seg = x; }
+        c.vvmax = seg;
+        int av, au;
+        vit3_step_bin(c, j, rid, s.lpv[wp][j], lp_u, &nv, &nu, &av, &au);
+        s.lpv[wp][j] = p.lt0;
+        s.Vv[wp][VIT_HW + j] = nv; s.Vu[wp][VIT_HW + j] = nu;
+        pr[j] = (uint16_t)av; pr[npb + j] = (uint16_t)au;
+        bestv = nv; bestk = j; vvb = nv;
+        if (nu > bestv) { bestv = nu; bestk = npb + j; }
+        live_v = nv >= thr; live_u = nu >= thr;
+      }
     }
+    prev_vmax = c.vmax;
     const int myrow = j < npb ? (int)s.rowid[j] : 0;
     if (!sparse) vit3_append(live_v, nv, j, myrow, s.Lv[wl], &s.cnt[wl][0], lane);
     vit3_append(live_u, nu, j, myrow, s.Lu[wl], &s.cnt[wl][1], lane);

@@ -210,6 +210,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     for (int j = 0; j < npb; ++j) { Vv[VIT_HW + j] = V[j].x; Vu[VIT_HW + j] = V[j].y; }
     long skipped = 0, listed = 0, n_sparse = 0, n_uniform = 0;
     bool sparse_prev = false;
+    double prev_vmax = 0.0;
     for (int64_t t = 1; t < T; ++t) {
       const int rp = (int)((t - 1) & 1), wp = (int)(t & 1), rl = (int)((t - 1) % 3), wl = (int)(t % 3), zl = (int)((t + 1) % 3);
       Vit3Step c;
@@ -261,10 +262,12 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
         }
         if (sparse) {
           const int w = j / 32;
-          const bool uni = (int)tb.lt_uniform.size() == VIT_TW && c.vmax <= tb.uniform_vmax && 32 * w >= 2 * VIT_HW &&
+          const bool uni = (int)tb.lt_uniform.size() == VIT_TW && prev_vmax <= tb.uniform_vmax && 32 * w >= 2 * VIT_HW &&
                            32 * w + 31 + 2 * VIT_HW <= npb - 1;
           if (uni) ++n_uniform;
-          vit4_step_unvoiced(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lp_unv[t], uni ? tb.lt_uniform.data() : nullptr, &nu, &au);
+          if (c.nv > VIT_LIST_MAX) c.vvmax = 0.0;
+          const VitBest2 bu = vit4_unvoiced_scan(c, j, rid.data() + (size_t)j * VIT_RID_REGS, uni ? tb.lt_uniform.data() : nullptr);
+          vit4_unvoiced_finish(bu, npb, tb.lt0, c.vmax, c.kstar, j, lp_unv[t], &nu, &au);
           if (lpv[j] == tb.lt0) Vv[(size_t)wp * VP + VIT_HW + j] = VIT_NEG;
           Vu[(size_t)wp * VP + VIT_HW + j] = nu;
           ptr[(size_t)t * 2 * npb + npb + j] = (uint16_t)au;
@@ -277,6 +280,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
         if (nu >= thr) { if (cnt[wl][1] < VIT_LIST_MAX) { VitLive e; e.v = nu; e.kb = j; e.row = tb.row_id[j]; Lu[(size_t)wl * VIT_LIST_MAX + cnt[wl][1]] = e; } ++cnt[wl][1]; }
       }
       sparse_prev = sparse;
+      prev_vmax = c.vmax;
       for (int q = 0; q < n_cand[t]; ++q) lpv[cand_bin[(size_t)t * g.kmax + q]] = tb.lt0;
     }
     const int lp_ = (int)((T - 1) & 1);
