@@ -514,6 +514,8 @@ struct alignas(16) Vit3Shared {
 __device__ __forceinline__ void vit3_append(bool live, double v, int kb, int row, VitLive* L, int* cnt, int lane) {
   const unsigned m = __ballot_sync(0xffffffffu, live);
   if (m == 0) return;
+  // already overflowed: the count only has to stay above VIT_LIST_MAX (the next step scans the band)
+  if (*reinterpret_cast<volatile int*>(cnt) > VIT_LIST_MAX) return;
   int base = 0;
   if (lane == 0) base = atomicAdd(cnt, __popc(m));
   base = __shfl_sync(0xffffffffu, base, 0);
@@ -686,7 +688,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     if (tid < nc_next) { s.lpv[wp ^ 1][nb_bin] = nb_lp; s.cbin[wp ^ 1][tid] = (uint16_t)nb_bin; s.clp[wp ^ 1][tid] = nb_lp; }
     nc_cur = nc_next;
     vit_warp_argmax_neg(bestv, bestk);
-    vvb = vit_warp_max(vvb);
+    if (!sparse) vvb = vit_warp_max(vvb);     // sparse: 0.0 everywhere
     if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; }
     __syncthreads();
   }
