@@ -27,6 +27,7 @@ struct PyinParams {
   const int32_t* sample_len;
   const int64_t* frame_off;   // [n_utts+1] pyin frames
   const int32_t* tile_off;    // [n_utts+1]
+  const int32_t* tile_map;    // [n_tiles] tile -> utterance (optional: null = binary search of tile_off)
   int32_t n_utts;
   // geometry
   int32_t F, W, hop;          // frame, win, hop
@@ -104,9 +105,13 @@ struct PyinTile {
 HD bool pyin_locate(const PyinParams& p, int tile, PyinTile* t) {
   int lo = 0, hi = p.n_utts;
   if (tile >= p.tile_off[p.n_utts]) return false;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (p.tile_off[mid] <= tile) lo = mid; else hi = mid;
+  if (p.tile_map) {
+    lo = p.tile_map[tile];      // one load instead of log2(n_utts) dependent ones
+  } else {
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (p.tile_off[mid] <= tile) lo = mid; else hi = mid;
+    }
   }
   t->utt = lo;
   t->T = (int32_t)(p.frame_off[lo + 1] - p.frame_off[lo]);
@@ -118,6 +123,7 @@ HD bool pyin_locate(const PyinParams& p, int tile, PyinTile* t) {
   return true;
 }
 
+constexpr int CMND_LOAD_U = 6;   // sample groups (of 4) a thread keeps in flight
 HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int tid, int nthr) {
   // energy terms first: asynchronous 4-byte copies on the device, consumed after the autocorrelation
   // (consecutive threads take consecutive frames of one lag: the global reads stay sector-coalesced)
@@ -143,25 +149,37 @@ HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
   // (src + p0 + i) is 16-byte aligned for every i % 4 == 0 iff (address / 4 + p0) % 4 == 0
   const bool aligned = (((reinterpret_cast<uintptr_t>(src) >> 2) + (uintptr_t)(t.p0 & 3)) & 3) == 0;
   const int n4 = p.ylen >> 2;      // ylen is a multiple of 4
-  for (int g4 = tid; g4 < n4; g4 += nthr) {
-    const int i = g4 << 2;
-    const int64_t q = t.p0 + i;
-    double* dst = s.yd + i;
-    float v0, v1, v2, v3;
-    if (aligned && q >= 0 && q + 3 < t.L) {
+  // in batches of CMND_LOAD_U groups per thread: all global loads of a batch are issued before the first
+  // conversion waits on one (one exposed memory latency per batch instead of one per group)
+  for (int g0 = tid; g0 < n4; g0 += CMND_LOAD_U * nthr) {
+    float v[CMND_LOAD_U][4];
+#pragma unroll
+    for (int u = 0; u < CMND_LOAD_U; ++u) {
+      const int g4 = g0 + u * nthr;
+      const int64_t q = t.p0 + ((int64_t)g4 << 2);
+      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+      if (g4 < n4) {
+        if (aligned && q >= 0 && q + 3 < t.L) {
 #if defined(__CUDA_ARCH__)
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + q));
-      v0 = v.x; v1 = v.y; v2 = v.z; v3 = v.w;
+          const float4 x = __ldg(reinterpret_cast<const float4*>(src + q));
+          v[u][0] = x.x; v[u][1] = x.y; v[u][2] = x.z; v[u][3] = x.w;
 #else
-      v0 = src[q]; v1 = src[q + 1]; v2 = src[q + 2]; v3 = src[q + 3];
+          v[u][0] = src[q]; v[u][1] = src[q + 1]; v[u][2] = src[q + 2]; v[u][3] = src[q + 3];
 #endif
-    } else {
-      v0 = (q >= 0 && q < t.L) ? src[q] : 0.f;
-      v1 = (q + 1 >= 0 && q + 1 < t.L) ? src[q + 1] : 0.f;
-      v2 = (q + 2 >= 0 && q + 2 < t.L) ? src[q + 2] : 0.f;
-      v3 = (q + 3 >= 0 && q + 3 < t.L) ? src[q + 3] : 0.f;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (q + e >= 0 && q + e < t.L) v[u][e] = src[q + e];
+        }
+      }
     }
-    dst[0] = (double)v0; dst[1] = (double)v1; dst[2] = (double)v2; dst[3] = (double)v3;
+#pragma unroll
+    for (int u = 0; u < CMND_LOAD_U; ++u) {
+      const int g4 = g0 + u * nthr;
+      if (g4 < n4) {
+        double* dst = s.yd + (g4 << 2);
+        dst[0] = (double)v[u][0]; dst[1] = (double)v[u][1]; dst[2] = (double)v[u][2]; dst[3] = (double)v[u][3];
+      }
+    }
   }
 }
 

@@ -415,6 +415,19 @@ __global__ void k_tile_offsets(const int64_t* frame_off, int32_t n_utts, int32_t
     __syncthreads();
   }
 }
+// tile -> utterance map from the tile prefix sums (one thread per tile, binary search once instead of in
+// every CTA of the consumer kernels)
+__global__ void k_tile_map(const int32_t* tile_off, int32_t n_utts, int32_t* map) {
+  const int n_tiles = tile_off[n_utts];
+  for (int tile = blockIdx.x * blockDim.x + threadIdx.x; tile < n_tiles; tile += gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_utts;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tile_off[mid] <= tile) lo = mid; else hi = mid;
+    }
+    map[tile] = lo;
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace roar

@@ -391,7 +391,7 @@ int roar_sup_pyin_geometry(const roar_sup_handle* h, int32_t out8[8]) {
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct PyinWs {
-  int32_t *tile_off, *etile_off, *order, *hist, *last_state, *n_cand;
+  int32_t *tile_off, *etile_off, *order, *hist, *last_state, *n_cand, *tile_map;
   double *big, *cand_lp, *lp_unv;
   float* energy;
   uint16_t* cand_bin;
@@ -408,6 +408,7 @@ static PyinWs pyin_ws_layout(const roar_sup_handle* h, int32_t n_utts, int64_t f
   w.hist = (int32_t*)take(sizeof(int32_t) * ((size_t)max_T + 2));
   w.last_state = (int32_t*)take(sizeof(int32_t) * (n_utts + 1));
   w.n_cand = (int32_t*)take(sizeof(int32_t) * (frames + 1));
+  w.tile_map = (int32_t*)take(sizeof(int32_t) * (size_t)(frames / h->pyin_FT + n_utts + 1));
   w.lp_unv = (double*)take(sizeof(double) * (frames + 1));
   w.cand_lp = (double*)take(sizeof(double) * (size_t)frames * g.kmax);
   w.cand_bin = (uint16_t*)take(sizeof(uint16_t) * (size_t)frames * g.kmax);
@@ -469,6 +470,8 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
   p.n_cand = w.n_cand; p.lp_unvoiced = w.lp_unv; p.voiced_prob = d_vprob; p.total_frames = total_frames;
   LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, p.FT, w.tile_off));
   const int64_t max_tiles = total_frames / p.FT + n_utts;
+  k_tile_map<<<(unsigned)((max_tiles + 255) / 256), 256, 0, st>>>(w.tile_off, n_utts, w.tile_map);
+  p.tile_map = w.tile_map;
   LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, ENERGY_FT, w.etile_off));
   LAUNCH(h, ROAR_K_PYIN_ENERGY, st, k_pyin_energy<<<(unsigned)(total_frames / ENERGY_FT + n_utts), ENERGY_THREADS, h->energy_smem, st>>>(p));
   LAUNCH(h, ROAR_K_PYIN_CMND, st, k_pyin_cmnd<<<(unsigned)max_tiles, CMND_THREADS, h->cmnd_smem, st>>>(p));
