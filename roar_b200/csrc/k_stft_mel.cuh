@@ -29,6 +29,7 @@ struct StftParams {
   const int32_t* sample_len;
   const int64_t* frame_off;   // [n_utts+1]
   const int32_t* tile_off;    // [n_utts+1] prefix sum of ceil(T_i / FT)
+  const int32_t* tile_map;    // [n_tiles] tile -> utterance (optional: null = binary search of tile_off)
   int32_t n_utts;
   float* logmel;              // may be null
   float* energy;              // may be null
@@ -98,9 +99,13 @@ struct StftTile {
 HD bool stft_locate(const StftParams& p, int tile, StftTile* t) {
   int lo = 0, hi = p.n_utts;
   if (tile >= p.tile_off[p.n_utts]) return false;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (p.tile_off[mid] <= tile) lo = mid; else hi = mid;
+  if (p.tile_map) {
+    lo = p.tile_map[tile];
+  } else {
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (p.tile_off[mid] <= tile) lo = mid; else hi = mid;
+    }
   }
   t->utt = lo;
   t->T = (int32_t)(p.frame_off[lo + 1] - p.frame_off[lo]);

@@ -444,6 +444,15 @@ int roar_sup_logmel_energy(roar_sup_handle* h, const float* d_audio, const int64
   p.tile_off = tile_off; p.n_utts = n_utts; p.logmel = d_logmel; p.energy = d_energy;
   LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, p.FT, tile_off));
   const int64_t max_tiles = total_frames / p.FT + n_utts;
+  {   // tile -> utterance map behind the prefix sums, when the caller's workspace has room for it
+    const size_t off_bytes = a256(sizeof(int32_t) * (size_t)(n_utts + 1));
+    const size_t lead = (size_t)((unsigned char*)tile_off - (unsigned char*)d_ws);
+    if (lead + off_bytes + sizeof(int32_t) * (size_t)(max_tiles + 1) <= ws_bytes) {
+      int32_t* map = (int32_t*)((unsigned char*)tile_off + off_bytes);
+      k_tile_map<<<(unsigned)((max_tiles + 255) / 256), 256, 0, st>>>(tile_off, n_utts, map);
+      p.tile_map = map;
+    }
+  }
   LAUNCH(h, ROAR_K_STFT_MEL, st, launch_stft(h, (unsigned)max_tiles, st, p));
   CUDA_TRY(cudaGetLastError());
   return 0;
