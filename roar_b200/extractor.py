@@ -155,8 +155,8 @@ class SupDataExtractor:
         np.cumsum(T, out=fo[1:])
         return torch.from_numpy(fo).to(self.device, non_blocking=True), fo
 
-    def _workspace(self, n_utts: int, total_samples: int, frames: int) -> torch.Tensor:
-        need = int(self.lib.roar_sup_workspace_bytes(self._h, n_utts, total_samples, frames))
+    def _workspace(self, n_utts: int, total_samples: int, frames: int, extra: int = 0) -> torch.Tensor:
+        need = int(self.lib.roar_sup_workspace_bytes(self._h, n_utts, total_samples, frames)) + int(extra)
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -183,11 +183,12 @@ class SupDataExtractor:
         total = int(fo[-1])
         lm = torch.empty(self.cfg.n_mels * total, dtype=torch.float32, device=self.device) if want_log_mel else None
         en = torch.empty(total, dtype=torch.float32, device=self.device) if want_energy else None
-        ws = self._workspace(batch.n_utts, batch.total_samples, 0)
+        # room for the tile -> utterance map behind the tile prefix sums (tiles hold >= 4 frames)
+        ws = self._workspace(batch.n_utts, batch.total_samples, 0, extra=total + 8 * batch.n_utts + 4096)
         _lib.check(self.lib.roar_sup_logmel_energy(
             self._h, _ptr(batch.audio), _ptr(batch.sample_off), _ptr(batch.sample_len), batch.n_utts,
             _ptr(d_fo), total, _ptr(lm), _ptr(en), _ptr(ws), ws.numel(), self._stream()))
-        self.kernel_launches += 2
+        self.kernel_launches += 3      # tile offsets, tile map, stft_mel
         return lm, en, fo
 
     def pyin(self, batch: PackedBatch):
@@ -205,8 +206,8 @@ class SupDataExtractor:
         _lib.check(self.lib.roar_sup_pyin(
             self._h, _ptr(batch.audio), _ptr(batch.sample_off), _ptr(batch.sample_len), batch.n_utts,
             _ptr(d_fo), total, int(T.max()), _ptr(f0), _ptr(vf), _ptr(vp), _ptr(ws), ws.numel(), self._stream()))
-        # 2 x tile offsets, energy, cmnd, probs, 3 x length sort, viterbi, backtrack
-        self.kernel_launches += 10
+        # 2 x tile offsets, tile map, energy, cmnd, probs, 3 x length sort, viterbi, backtrack
+        self.kernel_launches += 11
         return f0, vf, vp, fo
 
     def align_prior(self, text_lens, mel_lens, scaling_factor: float = 1.0):
