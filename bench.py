@@ -117,8 +117,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-utts", type=int, default=13100, help="utterances of the config-2 manifest per rank")
     ap.add_argument("--chunk-utts", type=int, default=0, help="utterances per device-resident call (0 = all)")
-    ap.add_argument("--e2e-chunk-utts", type=int, default=3280, help="largest streamed host chunk (utterances)")
+    ap.add_argument("--e2e-chunk-utts", type=int, default=2200, help="largest streamed host chunk (utterances)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-streams", type=int, default=2, choices=(1, 2),
+                    help="extractor objects / compute streams the streamed chunks alternate over (2: the occupancy "
+                         "tail of one chunk's kernels is filled by the next chunk's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cache-write-utts", type=int, default=512,
                     help="also time writing the .pt cache (5 files per utterance) for this many utterances; 0 = skip")
@@ -268,9 +271,21 @@ def main():
         out_stream = torch.cuda.Stream(dev)
         frame_cum = np.concatenate([[0], np.cumsum(1 + lens_h // HOP)])
 
+        # chunks alternate over `--e2e-streams` extractor objects, each with its own compute stream, handle and
+        # workspace: consecutive chunks are independent, so the tail of one chunk's kernels overlaps the head
+        # of the next chunk's
+        n_lane = args.e2e_streams
+        from roar_b200.extract_sup_data import merge_partials
+        lanes = [ex] + [SupDataExtractor(SupConfig(highfreq=8000.0), dev) for _ in range(n_lane - 1)]
+        lane_streams = [torch.cuda.Stream(dev) for _ in range(n_lane)]
+
         def step_e2e():
-            st = ex.new_pitch_partials(1)
             main = torch.cuda.current_stream()
+            sts = []
+            for e, cs in zip(lanes, lane_streams):
+                cs.wait_stream(main)
+                with torch.cuda.stream(cs):
+                    sts.append(e.new_pitch_partials(1))
             staged = {}
 
             def stage(i):
@@ -289,18 +304,25 @@ def main():
                 d, ev, lo = staged.pop(i)
                 if i + 1 < len(eb):
                     stage(i + 1)
-                main.wait_event(ev)
-                bt = ex.batch_from_device(d, offs_h[a:b] - lo, lens_h[a:b])
-                out = ex.extract(bt, text_lens=text_lens[a:b], stats=st)
-                done = torch.cuda.Event()
-                done.record(main)
+                e, cs = lanes[i % n_lane], lane_streams[i % n_lane]
+                with torch.cuda.stream(cs):
+                    cs.wait_event(ev)
+                    bt = e.batch_from_device(d, offs_h[a:b] - lo, lens_h[a:b])
+                    out = e.extract(bt, text_lens=text_lens[a:b], stats=sts[i % n_lane])
+                    done = torch.cuda.Event()
+                    done.record(cs)
                 f_lo, f_hi = int(frame_cum[a]), int(frame_cum[b])
                 with torch.cuda.stream(out_stream):
                     out_stream.wait_event(done)
                     for k in host_out:
                         m = N_MELS if k == "log_mel" else 1
                         host_out[k][m * f_lo:m * f_hi].copy_(out[k], non_blocking=True)
-                pending.append((out, d))     # keep device buffers alive until the copies are done
+                pending.append((out, d, bt))     # keep device buffers alive until the copies are done
+            for cs in lane_streams:
+                main.wait_stream(cs)
+            st = sts[0]
+            for o in sts[1:]:
+                st = merge_partials(st, o)
             if world > 1:
                 dist.all_reduce(st[:, :3], op=dist.ReduceOp.SUM)
             host_stats.copy_(st, non_blocking=True)
