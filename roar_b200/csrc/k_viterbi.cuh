@@ -506,6 +506,8 @@ struct alignas(16) Vit3Shared {
   int cnt[3][2];
   int pub_kstar, pad_;
   double pub_vmax, pub_thr;                  // block-wide values of the running step (written by the lead warp)
+  double nxt_lpu[2];                         // unvoiced observation / candidate count of frame f at [f & 1]
+  int nxt_nc[2];                             //   (written one step ahead by the prefetch warp)
   uint16_t cbin[2][VIT_KMAX_MAX];
   uint16_t rowid[VIT_NPB_MAX];
 };
@@ -561,10 +563,9 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     bestv = vv; bestk = j; vvb = vv;
     if (vu > bestv) { bestv = vu; bestk = npb + j; }
   }
-  double lp_u_next = 0.0;
   if (T > 1) {
     nc_cur = p.n_cand[f0 + 1];
-    lp_u_next = p.lp_unvoiced[f0 + 1];
+    if (tid == 0) { s.nxt_nc[1] = nc_cur; s.nxt_lpu[1] = p.lp_unvoiced[f0 + 1]; }
     if (tid < nc_cur) {
       const uint16_t b = p.cand_bin[(size_t)(f0 + 1) * kmax + tid];
       const double l = p.cand_lp[(size_t)(f0 + 1) * kmax + tid];
@@ -581,6 +582,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
   // memory; it signals named barrier 1 (bar.arrive) and the other warps wait on it (bar.sync) only
   // after their in-band work, which does not depend on those values.
   const int lead = nwarp >> 1;
+  const int pfw = lead > 0 ? lead - 1 : 0;            // prefetch warp
   double prev_vmax = 0.0;                              // vmax is strictly decreasing in t
   uint16_t* pr = p.ptr + (size_t)(f0 + 1) * (2 * npb);
   for (int t = 1; t < T; ++t, pr += 2 * npb) {
@@ -593,7 +595,8 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     c.lt2 = s.lt2; c.lt0 = p.lt0; c.lt_max = p.lt_max; c.npb = npb;
     c.vmax = 0.0; c.kstar = 0; c.vvmax = 0.0;
     if (tid < 2) s.cnt[zl][tid] = 0;
-    const double lp_u = lp_u_next;
+    const double lp_u = s.nxt_lpu[wp];
+    nc_cur = s.nxt_nc[wp];
     double thr = 0.0;
     if (warp == lead) {
       double vmax = lane < nwarp ? s.wv[rp][lane] : VIT_NEG;
@@ -607,15 +610,15 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       if (lane == 0) { s.pub_vmax = vmax; s.pub_thr = thr; s.pub_kstar = kstar; }
       asm volatile("bar.arrive 1, %0;" ::"r"(nthr) : "memory");
     }
-    // prefetch next frame's sparse observations (consumed after the band work)
-    int nc_next = 0; unsigned nb_bin = 0; double nb_lp = 0.0;
-    if (t + 1 < T) {
-      nc_next = p.n_cand[f0 + t + 1];
-      lp_u_next = p.lp_unvoiced[f0 + t + 1];
-      if (tid < nc_next) {
-        nb_bin = p.cand_bin[(size_t)(f0 + t + 1) * kmax + tid];
-        nb_lp = p.cand_lp[(size_t)(f0 + t + 1) * kmax + tid];
-      }
+    // one warp prefetches the next frame's sparse observations for the block (loads issued here, stored
+    // after the band work); lanes read list slots beyond n_cand too -- in bounds, discarded
+    const bool pf = warp == pfw && t + 1 < T;
+    int nc_next = 0; unsigned nb_bin = 0; double nb_lp = 0.0, nb_lpu = 0.0;
+    if (pf) {
+      const size_t fr = (size_t)(f0 + t + 1);
+      nc_next = p.n_cand[fr];
+      nb_lpu = p.lp_unvoiced[fr];
+      if (lane < kmax) { nb_bin = p.cand_bin[fr * kmax + lane]; nb_lp = p.cand_lp[fr * kmax + lane]; }
     }
     bestv = VIT_NEG; bestk = 0x7fffffff; vvb = VIT_NEG;
     bool live_v = false, live_u = false;
@@ -685,8 +688,16 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     const int myrow = j < npb ? (int)s.rowid[j] : 0;
     if (!sparse) vit3_append(live_v, nv, j, myrow, s.Lv[wl], &s.cnt[wl][0], lane);
     vit3_append(live_u, nu, j, myrow, s.Lu[wl], &s.cnt[wl][1], lane);
-    if (tid < nc_next) { s.lpv[wp ^ 1][nb_bin] = nb_lp; s.cbin[wp ^ 1][tid] = (uint16_t)nb_bin; s.clp[wp ^ 1][tid] = nb_lp; }
-    nc_cur = nc_next;
+    if (pf) {
+      if (lane == 0) { s.nxt_nc[wp ^ 1] = nc_next; s.nxt_lpu[wp ^ 1] = nb_lpu; }
+      if (lane < nc_next) { s.lpv[wp ^ 1][nb_bin] = nb_lp; s.cbin[wp ^ 1][lane] = (uint16_t)nb_bin; s.clp[wp ^ 1][lane] = nb_lp; }
+      for (int q = 32 + lane; q < nc_next; q += 32) {       // long candidate lists (rare)
+        const size_t fr = (size_t)(f0 + t + 1);
+        const unsigned b = p.cand_bin[fr * kmax + q];
+        const double l = p.cand_lp[fr * kmax + q];
+        s.lpv[wp ^ 1][b] = l; s.cbin[wp ^ 1][q] = (uint16_t)b; s.clp[wp ^ 1][q] = l;
+      }
+    }
     vit_warp_argmax_neg(bestv, bestk);
     if (!sparse) vvb = vit_warp_max(vvb);     // sparse: 0.0 everywhere
     if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; }
