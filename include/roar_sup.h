@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ROAR_SUP_ABI_VERSION 1
+#define ROAR_SUP_ABI_VERSION 2
 
 enum roar_sup_window { ROAR_WIN_HANN = 0, ROAR_WIN_HAMMING = 1, ROAR_WIN_BLACKMAN = 2,
                        ROAR_WIN_BARTLETT = 3, ROAR_WIN_NONE = 4 };
@@ -77,7 +77,7 @@ typedef struct roar_sup_config {
   /* pYIN (librosa.pyin keyword arguments as called at dataset.py:696-703) */
   double  pitch_fmin;
   double  pitch_fmax;
-  int32_t pyin_frame_length;  /* reference passes win_length */
+  int32_t pyin_frame_length;  /* reference passes win_length; 0 = mel-only handle (no pYIN tables, e.g. FilterbankFeatures) */
   int32_t pyin_win_length;    /* 0 => frame_length/2 */
   int32_t pyin_hop_length;    /* 0 => frame_length/4 (the reference does not pass hop_length) */
   int32_t n_thresholds;       /* 100 */
@@ -94,7 +94,7 @@ typedef struct roar_sup_handle roar_sup_handle;
 /* kernel ids for the optional per-kernel timing below */
 enum roar_sup_kernel { ROAR_K_TILE_OFFSETS = 0, ROAR_K_STFT_MEL = 1, ROAR_K_PYIN_CMND = 2, ROAR_K_PYIN_PROBS = 3,
                        ROAR_K_LEN_SORT = 4, ROAR_K_VITERBI = 5, ROAR_K_BACKTRACK = 6, ROAR_K_PRIOR = 7,
-                       ROAR_K_STATS = 8, ROAR_K_FBANK_NORM = 9, ROAR_K_PYIN_ENERGY = 10, ROAR_K_COUNT = 11 };  /* roar_sup_trim is not timed */
+                       ROAR_K_STATS = 8, ROAR_K_FBANK_NORM = 9, ROAR_K_PYIN_ENERGY = 10, ROAR_K_PCM16 = 11, ROAR_K_COUNT = 12 };  /* roar_sup_trim is not timed */
 
 /* Fill cfg with the reference's extraction defaults
  * (scripts/dataset_processing/tts/rasa/ds_conf/ds_for_fastpitch_align.yaml:12-27). */
@@ -130,9 +130,20 @@ int  roar_sup_host_window(const roar_sup_config* cfg, float* out /* [n_fft] */);
 int  roar_sup_host_pyin_log_transition(const roar_sup_config* cfg, double* out, int64_t n);
 int  roar_sup_host_pyin_beta_probs(const roar_sup_config* cfg, double* out /* [n_thresholds] */);
 
-/* Bytes of device workspace roar_sup_pyin / roar_sup_logmel_energy / roar_fbank_forward need. */
+/* Bytes of device workspace that serve every entry point taking a workspace (the maximum over their
+ * layouts): roar_sup_pyin for total_pyin_frames frames, roar_sup_logmel_energy, and
+ * roar_fbank_forward / roar_fbank_backward for a batch of n_utts rows. */
 size_t roar_sup_workspace_bytes(const roar_sup_handle* h, int32_t n_utts, int64_t total_samples,
                                 int64_t total_pyin_frames);
+/* Bytes roar_fbank_forward / roar_fbank_backward need for a batch of B rows. */
+size_t roar_fbank_workspace_bytes(const roar_sup_handle* h, int32_t B);
+
+/* 16-bit PCM ingest: replaces the integer -> float32 step of AudioSegment._convert_samples_to_float32
+ * (asr/parts/preprocessing/segment.py:140-153): d_audio[i] = d_pcm[i] / 2^15, exact.  The packed-batch
+ * layout (sample_off / sample_len) applies to d_audio unchanged, so a wav corpus travels host -> device
+ * at 2 bytes per sample. */
+int roar_sup_pcm16_to_f32(roar_sup_handle* h, const int16_t* d_pcm, int64_t n_samples, float* d_audio,
+                          void* stream);
 
 /* log-mel + energy: replaces TTSDataset.get_spec / get_log_mel / the energy line
  * (dataset.py:524-537, 751-753; torch.stft at :324-333).
@@ -209,6 +220,35 @@ int roar_fbank_forward(roar_sup_handle* h, const float* d_x, const int64_t* d_le
 int roar_fbank_backward(roar_sup_handle* h, const float* d_x, const int64_t* d_len, int32_t B, int64_t Lmax,
                         const float* d_grad_out, float* d_grad_x, void* d_workspace, size_t workspace_bytes,
                         void* stream);
+
+/* ---- host-side I/O of the extraction run (native threads, no device work) -------------------------------
+ * wav decoding: replaces AudioSegment.from_file for RIFF/WAVE input (asr/parts/preprocessing/segment.py:156-278,
+ * reached through WaveformFeaturizer.process, asr/parts/preprocessing/features.py:137-170): PCM 8/16/24/32 bit and
+ * IEEE float 32/64, any channel count, `offset` / `duration` as frame ranges. */
+typedef struct roar_wav_info {
+  int32_t sample_rate;   /* -1: the file could not be probed */
+  int32_t channels;
+  int32_t bits;
+  int32_t format;        /* 1 = integer PCM, 3 = IEEE float */
+  int64_t n_frames;
+  int64_t data_offset;   /* byte offset of the first frame */
+} roar_wav_info;
+/* Fills out[n]; returns the number of files that failed (their sample_rate is -1; roar_sup_last_error names one). */
+int roar_sup_wav_probe_batch(const char* const* paths, int32_t n, roar_wav_info* out, int32_t n_threads);
+/* Reads frames [first_frame[i], first_frame[i] + n_frames[i]) of file i to dst + dst_off[i] (elements):
+ *   as_pcm16 = 1: raw int16 (16-bit mono PCM files only) -- pair with roar_sup_pcm16_to_f32;
+ *   as_pcm16 = 0: float32 mono the way soundfile's float read scales (x / 2^(bits-1)); `channel` = -1 averages
+ *                 the channels (channel_selector="average"), otherwise selects one.
+ * dst is typically pinned host memory.  Returns the number of failed files. */
+int roar_sup_wav_read_batch(const char* const* paths, const roar_wav_info* info, int32_t n,
+                            const int64_t* first_frame, const int64_t* n_frames, int32_t channel,
+                            int32_t as_pcm16, void* dst, const int64_t* dst_off, int32_t n_threads);
+/* Cache writer: replaces torch.save(tensor, path) of the cached sup data (tts/data/dataset.py:656-657, 704-708,
+ * 752-753).  File i holds the contiguous float32 CPU tensor base[elem_off[i] ...] of shape shape3[3*i .. 3*i+rank[i])
+ * in torch's zip serialization (loadable by torch.load, weights_only or not); written to a temporary name and
+ * renamed into place, so an interrupted run never leaves a truncated cache file.  Returns the number of failures. */
+int roar_sup_pt_write_batch(const float* base, int32_t n_files, const int64_t* elem_off, const int32_t* rank,
+                            const int64_t* shape3, const char* const* paths, int32_t n_threads);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,11 @@ SYMBOLS = [
     "roar_sup_pyin", "roar_sup_align_prior", "roar_sup_align_prior_interp", "roar_sup_pitch_partials_init", "roar_sup_pitch_partials",
     "roar_sup_pitch_partials_grouped", "roar_fbank_out_frames", "roar_fbank_forward",
     "roar_sup_set_profiling", "roar_sup_profile_read", "roar_sup_trim", "roar_fbank_backward",
+    "roar_fbank_workspace_bytes", "roar_sup_pcm16_to_f32",
+    "roar_sup_wav_probe_batch", "roar_sup_wav_read_batch", "roar_sup_pt_write_batch",
 ]
+ABI_VERSION = 2
+N_KERNEL_IDS = 12      # ROAR_K_COUNT
 
 _lib = None
 
@@ -67,9 +71,15 @@ def load():
     lib.roar_fbank_out_frames.restype = i64
     lib.roar_fbank_forward.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp, ctypes.c_size_t, vp]
     lib.roar_fbank_backward.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.roar_fbank_workspace_bytes.argtypes = [vp, i32]
+    lib.roar_fbank_workspace_bytes.restype = ctypes.c_size_t
+    lib.roar_sup_pcm16_to_f32.argtypes = [vp, vp, i64, vp, vp]
+    lib.roar_sup_wav_probe_batch.argtypes = [vp, i32, vp, i32]
+    lib.roar_sup_wav_read_batch.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp, i32]
+    lib.roar_sup_pt_write_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32]
     lib.roar_sup_set_profiling.argtypes = [vp, ctypes.c_int]
     lib.roar_sup_profile_read.argtypes = [vp, vp, vp, ctypes.c_int]
-    if lib.roar_sup_abi_version() != 1:
+    if lib.roar_sup_abi_version() != ABI_VERSION:
         raise RoarSupError("libroar_sup.so ABI version mismatch")
     _lib = lib
     return lib

@@ -64,6 +64,7 @@ class SupConfig:
     energy_mode: str = "spectrum"        # "spectrum": TTSDataset energy; "features": EnergyFeaturizer (norm over mel axis)
     pitch_fmin: float = PITCH_FMIN_C2
     pitch_fmax: float = PITCH_FMAX_C7
+    pyin: bool = True                         # False: mel-only handle (no pYIN tables; FilterbankFeatures)
     pyin_frame_length: Optional[int] = None   # None -> win_length (what TTSDataset passes)
     pyin_win_length: Optional[int] = None
     pyin_hop_length: Optional[int] = None     # None -> frame_length // 4 (TTSDataset does not pass hop)
@@ -123,7 +124,7 @@ class SupConfig:
         c.energy_mode = 1 if self.energy_mode == "features" else 0
         c.pitch_fmin = float(self.pitch_fmin)
         c.pitch_fmax = float(self.pitch_fmax)
-        c.pyin_frame_length = int(self.pyin_frame)
+        c.pyin_frame_length = int(self.pyin_frame) if self.pyin else 0
         c.pyin_win_length = int(self.pyin_win_length or 0)
         c.pyin_hop_length = int(self.pyin_hop_length or 0)
         c.n_thresholds = int(self.n_thresholds)

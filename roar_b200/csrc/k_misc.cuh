@@ -216,6 +216,27 @@ __global__ void __launch_bounds__(256) k_trim(const TrimParams p) {
 #endif  // __CUDACC__
 
 #ifdef __CUDACC__
+// ------------------------------------------------------------------------------------ K0 16-bit PCM ingest
+// int16 -> float32 / 2^15 (exact).  Grid-stride, 8 samples per thread per trip: one 16-byte load, two
+// 16-byte stores when both pointers are 16-byte aligned; scalar head/tail otherwise.
+__global__ void __launch_bounds__(256) k_pcm16_to_f32(const int16_t* __restrict__ pcm, int64_t n, float* __restrict__ out) {
+  const float sc = 1.0f / 32768.0f;
+  const bool vec = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const int64_t n8 = vec ? n / 8 : 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(pcm) + i);
+    float4 a, b;
+    a.x = (float)(short)(v.x & 0xffff) * sc; a.y = (float)(short)(v.x >> 16) * sc;
+    a.z = (float)(short)(v.y & 0xffff) * sc; a.w = (float)(short)(v.y >> 16) * sc;
+    b.x = (float)(short)(v.z & 0xffff) * sc; b.y = (float)(short)(v.z >> 16) * sc;
+    b.z = (float)(short)(v.w & 0xffff) * sc; b.w = (float)(short)(v.w >> 16) * sc;
+    reinterpret_cast<float4*>(out)[2 * i] = a;
+    reinterpret_cast<float4*>(out)[2 * i + 1] = b;
+  }
+  for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)pcm[i] * sc;
+}
+
 // ------------------------------------------------------------------------------------ K5 stats
 // get_pitch_stats (scripts/dataset_processing/tts/extract_sup_data.py:8-13): mean / unbiased std /
 // min / max over pitch != 0.  Produces float64 partials (sum, sumsq, count, min, max) that the ranks

@@ -50,8 +50,10 @@ inline std::string validate(const roar_sup_config& c) {
   if (c.window < 0 || c.window > 4) return "unknown window";
   if (c.exact_pad && (c.hop_length % 2 == 1)) return "exact_pad requires an even hop_length";
   if (c.pitch_fmin <= 0 || c.pitch_fmax <= c.pitch_fmin) return "need 0 < pitch_fmin < pitch_fmax";
-  if (!is_pow2(c.pyin_frame_length) || c.pyin_frame_length < 64 || c.pyin_frame_length > 4096)
-    return "pyin_frame_length must be a power of two in [64, 4096]";
+  // pyin_frame_length == 0: a mel-only handle (FilterbankFeatures) -- no pYIN tables, roar_sup_pyin is rejected
+  if (c.pyin_frame_length != 0 &&
+      (!is_pow2(c.pyin_frame_length) || c.pyin_frame_length < 64 || c.pyin_frame_length > 4096))
+    return "pyin_frame_length must be 0 (no pYIN) or a power of two in [64, 4096]";
   if (c.n_thresholds <= 0 || c.n_thresholds > 256) return "n_thresholds must be in (0, 256]";
   return "";
 }
@@ -61,6 +63,11 @@ inline Geometry geometry(const roar_sup_config& c) {
   g.n_fft = c.n_fft; g.win = c.win_length; g.hop = c.hop_length;
   g.n_bins = c.n_fft / 2 + 1; g.n_mels = c.n_mels; g.M = c.n_fft / 2;
   g.pf = c.pyin_frame_length;
+  if (g.pf == 0) {   // mel-only handle
+    g.pw = g.ph = g.min_period = g.max_period = g.n_lags = g.npb = g.nbps = g.tw = g.hw = g.kmax = 0;
+    g.n_thr = c.n_thresholds;
+    return g;
+  }
   g.pw = c.pyin_win_length > 0 ? c.pyin_win_length : g.pf / 2;
   g.ph = c.pyin_hop_length > 0 ? c.pyin_hop_length : g.pf / 4;
   g.min_period = (int)std::floor((double)c.sample_rate / c.pitch_fmax);

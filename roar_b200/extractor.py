@@ -117,6 +117,25 @@ class SupDataExtractor:
                            torch.from_numpy(np.ascontiguousarray(lens, dtype=np.int32)).to(self.device, non_blocking=True),
                            np.asarray(lens, dtype=np.int64), np.asarray(offs, dtype=np.int64))
 
+    def pcm16_to_f32(self, pcm: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Device int16 PCM -> float32 ``x / 2**15`` (``segment.py:140-153``), on the current stream."""
+        assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()
+        if out is None:
+            out = torch.empty(pcm.numel(), dtype=torch.float32, device=pcm.device)
+        _lib.check(self.lib.roar_sup_pcm16_to_f32(self._h, _ptr(pcm), pcm.numel(), _ptr(out), self._stream()))
+        self.kernel_launches += 1
+        return out
+
+    def pack_pcm16_from_host_buffer(self, host: torch.Tensor, offs: np.ndarray, lens: np.ndarray) -> PackedBatch:
+        """Packed 16-bit PCM in (pinned) host memory -> device float32 batch: the copy moves 2 bytes per
+        sample, the integer -> float step of the wav decoder runs on the GPU."""
+        assert host.dtype == torch.int16
+        audio = self.pcm16_to_f32(host.to(self.device, non_blocking=True))
+        return PackedBatch(audio,
+                           torch.from_numpy(np.ascontiguousarray(offs, dtype=np.int64)).to(self.device, non_blocking=True),
+                           torch.from_numpy(np.ascontiguousarray(lens, dtype=np.int32)).to(self.device, non_blocking=True),
+                           np.asarray(lens, dtype=np.int64), np.asarray(offs, dtype=np.int64))
+
     def batch_from_device(self, audio: torch.Tensor, offs: np.ndarray, lens: np.ndarray) -> PackedBatch:
         assert audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous()
         return PackedBatch(audio,

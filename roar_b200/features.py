@@ -86,8 +86,7 @@ class FilterbankFeatures(nn.Module):
             log_guard=guard, exact_pad=exact_pad, preemph=preemph,
             normalize=normalize if normalize in ("per_feature", "all_features") else None,
             pad_value=pad_value, pad_to=int(pad_to) if pad_to else 0,
-            # pYIN tables are built per handle; any valid frame length will do for this module
-            pyin_frame_length=max(256, self.n_fft))
+            pyin=False)      # mel-only handle: no pYIN tables, none of pYIN's geometry limits
         self._c = self._cfg.to_c()
         self._lib = _lib.load()
         self._h = None
@@ -145,21 +144,26 @@ class FilterbankFeatures(nn.Module):
         Tpad = int(self._lib.roar_fbank_out_frames(h, Lmax))
         out = torch.empty(B, self.nfilt, Tpad, dtype=torch.float32, device=x.device)
         out_len = torch.empty(B, dtype=torch.int64, device=x.device)
-        need = int(self._lib.roar_sup_workspace_bytes(h, B, B * Lmax, 0))
-        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        ws = self._workspace(h, B, x.device)
         _lib.check(self._lib.roar_fbank_forward(
-            h, _ptr(x), _ptr(lens), B, Lmax, _ptr(out), _ptr(out_len), _ptr(self._ws), self._ws.numel(),
+            h, _ptr(x), _ptr(lens), B, Lmax, _ptr(out), _ptr(out_len), _ptr(ws), ws.numel(),
             ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
         return out, out_len
+
+    def _workspace(self, h, B, device):
+        need = int(self._lib.roar_fbank_workspace_bytes(h, B))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
 
     def _run_backward(self, x, lens, grad_out):
         B, Lmax = x.shape
         h = self._handle(x.device)
         gx = torch.empty_like(x)
+        ws = self._workspace(h, B, x.device)
         _lib.check(self._lib.roar_fbank_backward(
-            h, _ptr(x), _ptr(lens), B, Lmax, _ptr(grad_out.contiguous().float()), _ptr(gx), _ptr(self._ws),
-            self._ws.numel(), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+            h, _ptr(x), _ptr(lens), B, Lmax, _ptr(grad_out.contiguous().float()), _ptr(gx), _ptr(ws),
+            ws.numel(), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
         return gx
 
     def forward(self, x, seq_len, linear_spec=False):

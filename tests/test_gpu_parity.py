@@ -41,7 +41,7 @@ def test_library_loaded_is_in_tree():
     from roar_b200 import _lib
     lib = _lib.load()
     assert os.path.dirname(_lib.LIB_PATH).endswith("roar_b200")
-    assert lib.roar_sup_abi_version() == 1
+    assert lib.roar_sup_abi_version() == _lib.ABI_VERSION
 
 
 def test_logmel_energy_golden(ex, golden_dir):
