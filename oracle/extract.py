@@ -34,15 +34,15 @@ def _worker_init():
 
 
 def _worker(args):
-    seed, utt_id, n_samples, sr, speaker, text_len = args
+    seed, utt_id, n_samples, sr, speaker, text_len, kw = args
     from roar_b200 import synth
     y = synth.synth_utterance(seed, utt_id, n_samples, sr, speaker)
-    out = extract_utterance(y, text_len, sr=sr)
+    out = extract_utterance(y, text_len, sr=sr, **kw)
     p = out["pitch"]
     return n_samples / sr, float(p[p != 0].sum()), int((p != 0).sum())
 
 
-def timed_cpu_extraction(corpus="C2", first=0, count=8, processes=None):
+def timed_cpu_extraction(corpus="C2", first=0, count=8, processes=None, **kw):
     """Run ``count`` utterances of ``corpus`` through the reference-style CPU path on ``processes``
     worker processes (one utterance per task, like ``DataLoader(batch_size=1, num_workers=N)``,
     ``extract_sup_data.py:66-71``).  -> (audio_seconds, wall_seconds, processes)."""
@@ -54,10 +54,10 @@ def timed_cpu_extraction(corpus="C2", first=0, count=8, processes=None):
     processes = processes or os.cpu_count() or 1
     spec_ = synth.CORPORA[corpus]
     man = synth.corpus_manifest(corpus, first + count)[first:first + count]
-    tasks = [(spec_["seed"], u.utt_id, u.n_samples, spec_["sr"], u.speaker, u.text_len) for u in man]
+    tasks = [(spec_["seed"], u.utt_id, u.n_samples, spec_["sr"], u.speaker, u.text_len, kw) for u in man]
     # compile the numba kernels once in the parent so forked workers inherit them
-    pyin.pyin(np.zeros(4096, np.float32), 65.4, 2093.0, sr=spec_["sr"], frame_length=1024, fill_na=0.0,
-              dense_viterbi=True)
+    pyin.pyin(np.zeros(8192, np.float32), 65.4, 2093.0, sr=spec_["sr"], frame_length=kw.get("win_length", 1024),
+              fill_na=0.0, dense_viterbi=True)
     ctx = mp.get_context("fork")
     with ctx.Pool(processes, initializer=_worker_init) as pool:
         pool.map(_worker, tasks[:min(len(tasks), processes)][:0])  # spin the workers up (no work)

@@ -70,7 +70,7 @@ class FilterbankFeaturesOracle:
     def _guard(self, x):
         v = self.log_zero_guard_value
         if isinstance(v, str):
-            return {"tiny": torch.finfo(x.dtype).tiny, "eps": torch.finfo(x.dtype).eps}[v]
+            return {"tiny": torch.finfo(torch.float32).tiny, "eps": torch.finfo(torch.float32).eps}[v]
         return v
 
     def get_seq_len(self, seq_len):
@@ -78,8 +78,11 @@ class FilterbankFeaturesOracle:
         seq_len = torch.floor_divide((seq_len + pad_amount - self.n_fft), self.hop_length) + 1
         return seq_len.to(dtype=torch.long)
 
-    def forward(self, x, seq_len, linear_spec=False):
-        x = torch.as_tensor(np.asarray(x, dtype=np.float32)).clone()
+    def forward(self, x, seq_len, linear_spec=False, dtype=torch.float32):
+        """``dtype=torch.float64`` evaluates the SAME statements on the same float32 input and tables in double
+        precision: the exact-arithmetic yardstick against which the float32 spread of the reference's own
+        ``torch.stft`` path is measured (tests)."""
+        x = torch.as_tensor(np.asarray(x, dtype=np.float32)).clone().to(dtype)
         seq_len = self.get_seq_len(torch.as_tensor(np.asarray(seq_len)))
         if self.stft_pad_amount is not None:
             x = torch.nn.functional.pad(x.unsqueeze(1), (self.stft_pad_amount, self.stft_pad_amount),
@@ -88,7 +91,7 @@ class FilterbankFeaturesOracle:
             x = torch.cat((x[:, 0].unsqueeze(1), x[:, 1:] - self.preemph * x[:, :-1]), dim=1)
         x = torch.stft(x, n_fft=self.n_fft, hop_length=self.hop_length, win_length=self.win_length,
                        center=False if self.exact_pad else True,
-                       window=self.window.to(dtype=torch.float) if self.window is not None else None,
+                       window=self.window.to(dtype=dtype) if self.window is not None else None,
                        return_complex=True)
         guard = 0 if not self.use_grads else CONSTANT
         x = torch.view_as_real(x)

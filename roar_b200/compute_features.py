@@ -105,15 +105,31 @@ def make_batches(lengths, max_samples: int) -> List[np.ndarray]:
 
 def run(featurizers: Dict[str, Any], entries: List[Dict[str, Any]], audio_dir: Path, feature_dir: Path,
         batch_audio_seconds: float = 2000.0) -> None:
+    from concurrent.futures import ThreadPoolExecutor
+
+    from . import host_io
     from .extract_sup_data import load_wav
     if not entries:
         return
     sr = next(iter(featurizers.values())).sample_rate
-    wavs = [load_wav(str(F.get_abs_rel_paths(Path(e["audio_filepath"]), audio_dir)[0]), sr) for e in entries]
-    for b in make_batches([len(w) for w in wavs], int(batch_audio_seconds * sr)):
-        sub_e, sub_w = [entries[i] for i in b], [wavs[i] for i in b]
-        for feature_name, featurizer in featurizers.items():
-            featurizer.save_batch(sub_e, audio_dir, feature_dir, wavs=sub_w)
+    paths = [str(F.get_abs_rel_paths(Path(e["audio_filepath"]), audio_dir)[0]) for e in entries]
+    # batch composition from the wav headers; only one batch of audio (plus the one being prefetched) is ever
+    # decoded in host memory, whatever the manifest size
+    lengths = host_io.wav_probe(paths)["n_frames"].astype(np.int64)
+    batches = make_batches(lengths, int(batch_audio_seconds * sr))
+
+    def decode(b):
+        return [load_wav(paths[i], sr) for i in b]
+
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        fut = pool.submit(decode, batches[0])
+        for k, b in enumerate(batches):
+            sub_w = fut.result()
+            if k + 1 < len(batches):
+                fut = pool.submit(decode, batches[k + 1])
+            sub_e = [entries[i] for i in b]
+            for feature_name, featurizer in featurizers.items():
+                featurizer.save_batch(sub_e, audio_dir, feature_dir, wavs=sub_w)
 
 
 def main(argv=None):

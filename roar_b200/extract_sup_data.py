@@ -17,15 +17,28 @@ positionally); statistics are accumulated in float64 and a
 ranks; ``pitch_stats.json`` (``default`` + per speaker, the format ``pitch_stats_path`` reads,
 ``dataset.py:485-487, 720-733``) is written next to the cache.
 ``dataset.trim=true`` (+ ``trim_ref``, ``trim_top_db``, ``trim_frame_length``, ``trim_hop_length``) runs
-``librosa.effects.trim`` on the GPU (``roar_sup_trim``).  Out of scope:
-resampling -- the audio must already be at ``dataset.sample_rate``; wav decoding uses
-``scipy.io.wavfile`` on the host.
+``librosa.effects.trim`` on the GPU (``roar_sup_trim``).
+
+The run is a bounded-memory stream (the reference overlaps decode and compute through
+``DataLoader(num_workers=...)``, ``extract_sup_data.py:66-71``):
+
+    native wav decode threads -> ring of pinned staging buffers -> H2D (16-bit PCM stays int16, converted on the
+    GPU) -> kernels -> async D2H into pinned output buffers -> native ``.pt`` writer threads
+
+with ``pipeline_depth`` batches in flight, so host memory is a few staging buffers whatever the manifest size and
+the GPU never waits for a whole shard to decode.  ``align_prior_matrix`` is accepted in ``sup_data_types`` (the
+reference's ds_conf lists it) but nothing is computed for it here: the reference never caches it and discards the
+batch element (``extract_sup_data.py:24,29-30``).  A manifest entry's ``mel_filepath`` that exists counts as the
+cached log-mel (``dataset.py:646-649``).
 """
 import json
 import os
 import re
 import sys
+import heapq
+import queue
 import threading
+import time
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 from typing import Dict, List, Optional
@@ -49,8 +62,9 @@ DEFAULTS = {
         "n_mels": 80, "lowfreq": 0, "highfreq": 8000, "max_duration": None, "min_duration": 0.1,
         "ignore_file": None, "trim": False, "pitch_fmin": PITCH_FMIN_C2, "pitch_fmax": PITCH_FMAX_C7,
     },
-    "batch_audio_seconds": 4000.0,   # audio per device call (bounds the Viterbi scratch)
-    "writer_processes": None,        # worker processes writing the .pt cache (default: min(16, cores))
+    "batch_audio_seconds": 12000.0,  # audio per device call (bounds the Viterbi scratch and the staging buffers)
+    "pipeline_depth": 3,             # staging-buffer sets in flight: decode | compute | write
+    "writer_threads": None,          # native .pt writer threads (default: min(16, cores))
 }
 
 
@@ -173,26 +187,39 @@ def rel_audio_id(path: str, base_dir: Path) -> str:
     return str(Path(path).relative_to(base_dir).with_suffix("")).replace("/", "_")
 
 
-def read_manifest(path: str, min_duration=None, max_duration=None, ignore_file=None) -> List[dict]:
+def read_manifest(path, min_duration=None, max_duration=None, ignore_file=None) -> List[dict]:
+    """Manifest loading and pruning with the reference's rules (``dataset.py:215-275, 367-406``):
+    ``path`` is one manifest or a list of them; the duration filter applies only when EVERY entry carries a
+    ``duration`` (``total_duration is not None``); ``ignore_file`` is a pickled list of ``audio_filepath``
+    strings compared verbatim (each listed path prunes one entry)."""
+    paths = [path] if isinstance(path, (str, os.PathLike)) else list(path)
+    data = []
+    all_have_duration = True
+    for mf in paths:
+        with open(Path(mf).expanduser(), encoding="utf-8") as f:
+            for line in f:
+                line = line.strip()
+                if not line:
+                    continue
+                item = json.loads(line)
+                if item.get("duration") is None:
+                    all_have_duration = False
+                data.append(item)
     ignore = set()
     if ignore_file:
         import pickle
-        with open(ignore_file, "rb") as f:
+        with open(Path(ignore_file).expanduser(), "rb") as f:
             ignore = set(pickle.load(f))
     out = []
-    with open(path, encoding="utf-8") as f:
-        for line in f:
-            line = line.strip()
-            if not line:
+    for item in data:
+        if all_have_duration:
+            dur = item["duration"]
+            if (min_duration and dur < min_duration) or (max_duration and dur > max_duration):
                 continue
-            item = json.loads(line)
-            dur = item.get("duration")
-            if dur is not None:  # filter_by_duration, dataset.py:367-406
-                if (min_duration and dur < min_duration) or (max_duration and dur > max_duration):
-                    continue
-            if Path(item["audio_filepath"]).stem in ignore:
-                continue
-            out.append(item)
+        if ignore_file and item["audio_filepath"] in ignore:
+            ignore.remove(item["audio_filepath"])
+            continue
+        out.append(item)
     return out
 
 
@@ -207,32 +234,35 @@ def text_length(item: dict) -> int:
 
 
 def load_wav(path: str, sample_rate: int) -> np.ndarray:
-    """float32 mono in [-1, 1] like ``AudioSegment.from_file`` (``segment.py:156-278``) for wav files."""
-    from scipy.io import wavfile
-    sr, x = wavfile.read(path)
+    """float32 mono in [-1, 1] like ``AudioSegment.from_file`` (``segment.py:156-278``) for wav files
+    (native decoder, channels averaged)."""
+    from . import host_io
+    x, sr = host_io.load_wav(path)
     if sr != sample_rate:
-        raise ValueError(f"{path}: sample rate {sr} != dataset.sample_rate {sample_rate}; resampling is outside "
-                         "the accelerated path (SURVEY.md section 8f, N3) -- resample the corpus first")
-    if x.dtype.kind == "i":
-        x = x.astype(np.float32) / float(2 ** (8 * x.dtype.itemsize - 1))
-    elif x.dtype.kind == "u":
-        x = (x.astype(np.float32) - 128.0) / 128.0
-    else:
-        x = x.astype(np.float32)
-    if x.ndim > 1:
-        x = x.mean(axis=1)
-    return np.ascontiguousarray(x, dtype=np.float32)
+        raise ValueError(f"{path}: sample rate {sr} != requested {sample_rate}")
+    return x
 
 
 def shard_indices(durations, world: int, rank: int) -> np.ndarray:
-    """Length-bucketed sharding: sort by duration, deal round-robin -> equal audio and equal length mix on
-    every rank, no inter-GPU traffic.  Deterministic; ranks partition the set."""
-    order = np.argsort(-np.asarray(durations, dtype=np.float64), kind="stable")
-    return np.sort(order[rank::world])
+    """Utterance -> rank assignment with no inter-GPU traffic: longest-processing-time
+    greedy on the durations -- utterances by decreasing duration, each to the rank with the least audio so far
+    (ties: lowest rank).  Every rank ends within one utterance of the same total audio and gets the same length
+    mix.  Deterministic; the ranks partition the set.  -> sorted indices of ``rank``."""
+    d = np.asarray(durations, dtype=np.float64)
+    if world <= 1:
+        return np.arange(len(d))
+    order = np.argsort(-d, kind="stable")
+    owner = np.empty(len(d), dtype=np.int32)
+    heap = [(0.0, r) for r in range(world)]
+    for i in order:
+        load, r = heap[0]
+        owner[i] = r
+        heapq.heapreplace(heap, (load + float(d[i]), r))
+    return np.flatnonzero(owner == rank)
 
 
 def make_batches(lengths, max_samples: int) -> List[np.ndarray]:
-    """Group utterance indices (already length-sorted descending within the shard) into device calls."""
+    """Group utterance indices (length-sorted descending) into device calls of at most ``max_samples``."""
     idx = np.argsort(-np.asarray(lengths), kind="stable")
     batches, cur, tot = [], [], 0
     for i in idx:
@@ -293,94 +323,75 @@ def stats_from_partials(row) -> Optional[Dict[str, float]]:
     return {"pitch_mean": mean, "pitch_std": std, "pitch_min": mn, "pitch_max": mx}
 
 
-# ------------------------------------------------------------------------------------ cache writer
-class CacheWriter:
-    """Writes ``torch.save`` files from a thread pool; temp file + rename keeps the cache idempotent
-    under interruption (failure detection)."""
+# ------------------------------------------------------------------------------------ staging
+class StagingSlot:
+    """One set of pinned host buffers: packed input audio (int16 PCM or float32) and one flat float32 output
+    buffer per cached type.  Buffers grow to the largest batch seen and are reused."""
 
-    def __init__(self, threads: int):
-        self.pool = ThreadPoolExecutor(max_workers=max(1, threads))
-        self.futures = []
-        self.lock = threading.Lock()
+    def __init__(self):
+        self.bufs: Dict[str, torch.Tensor] = {}
+        self.free = threading.Event()
+        self.free.set()
 
-    @staticmethod
-    def _save(tensor: torch.Tensor, path: Path):
-        tmp = path.with_suffix(path.suffix + f".tmp{os.getpid()}")
-        torch.save(tensor, tmp)
-        os.replace(tmp, path)
-
-    def submit(self, tensor: torch.Tensor, path: Path):
-        self.futures.append(self.pool.submit(self._save, tensor, path))
-
-    def drain(self):
-        for f in self.futures:
-            f.result()
-        self.futures = []
+    def buf(self, name: str, n: int, dtype) -> torch.Tensor:
+        t = self.bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            self.bufs[name] = None
+            t = torch.empty(max(n, 1), dtype=dtype, pin_memory=torch.cuda.is_available())
+            self.bufs[name] = t
+        return t
 
 
-def _save_range(args):
-    """Worker: write the cache files of utterances [lo, hi) of one batch (flat host tensors in shared memory)."""
-    host, jobs, n_mels = args
-    torch.set_num_threads(1)
-    n = 0
-    for t, a, e, path in jobs:
-        if t == "log_mel":
-            ten = host[t][n_mels * a: n_mels * e].view(1, n_mels, e - a).clone()
-        else:
-            ten = host[t][a:e].clone()
-        CacheWriter._save(ten, Path(path))
-        n += 1
-    return n
+def _zero_gaps(hv: np.ndarray, offs: np.ndarray, lens: np.ndarray, total: int):
+    """The alignment gaps between packed utterances (<= 3 samples each) are staged by the kernels' bulk copies:
+    keep them finite."""
+    ends = offs + lens
+    nxt = np.concatenate([offs[1:], [total]])
+    for k in range(int((nxt - ends).max()) if len(offs) else 0):
+        m = nxt - ends > k
+        hv[ends[m] + k] = 0
 
 
-class ParallelCacheWriter:
-    """``torch.save`` of ~5 small files per utterance is pickling-bound (GIL), so a thread pool tops out at a few
-    thousand files/s; this writer hands contiguous utterance ranges of a batch to worker PROCESSES, the flat
-    host tensors travelling once per batch through shared memory."""
+class LoadedBatch:
+    __slots__ = ("slot", "idx", "host", "offs", "lens", "total", "pcm16")
 
-    def __init__(self, processes: int):
-        import torch.multiprocessing as mp      # tensors in shared memory travel by handle, not by value
-        self.n = max(1, processes)
-        self.pool = mp.get_context("fork").Pool(self.n) if self.n > 1 else None
-        self.pending = []
 
-    def submit_batch(self, host: Dict[str, torch.Tensor], jobs: List[tuple], n_mels: int):
-        """jobs: (type, frame_begin, frame_end, path) per file, grouped by utterance order."""
-        if not jobs:
-            return
-        if self.pool is None:
-            _save_range((host, jobs, n_mels))
-            return
-        for t in host.values():
-            t.share_memory_()
-        per = (len(jobs) + self.n - 1) // self.n
-        for lo in range(0, len(jobs), per):
-            self.pending.append(self.pool.apply_async(_save_range, ((host, jobs[lo:lo + per], n_mels),)))
-
-    def drain(self):
-        for r in self.pending:
-            r.get()
-        self.pending = []
-
-    def close(self):
-        self.drain()
-        if self.pool is not None:
-            self.pool.close()
-            self.pool.join()
-            self.pool = None
+def load_batch(slot: StagingSlot, paths: List[str], sample_rate: int, threads: int) -> LoadedBatch:
+    """Decode one batch of wav files into ``slot`` (native threads).  16-bit mono PCM stays int16 (2 bytes per
+    sample over PCIe, ``x / 2**15`` on the GPU); any other encoding is decoded to float32 mono on the host."""
+    from . import host_io
+    from .extractor import pack_layout
+    info = host_io.wav_probe(paths, threads)
+    bad = np.flatnonzero(info["sample_rate"] != sample_rate)
+    if len(bad):
+        raise ValueError(f"{paths[int(bad[0])]}: sample rate {int(info['sample_rate'][bad[0]])} != dataset.sample_rate "
+                         f"{sample_rate}; resample the corpus first (roar_b200.resample)")
+    lens = info["n_frames"].astype(np.int64)
+    offs, total = pack_layout(lens)
+    pcm16 = bool(host_io.is_pcm16_mono(info).all())
+    host = slot.buf("pcm16" if pcm16 else "f32", total, torch.int16 if pcm16 else torch.float32)
+    host_io.wav_read(paths, info, np.zeros(len(paths), np.int64), lens, host, offs, -1, threads)
+    _zero_gaps(host.numpy(), offs, lens, total)
+    lb = LoadedBatch()
+    lb.slot, lb.host, lb.offs, lb.lens, lb.total, lb.pcm16 = slot, host, offs, lens, total, pcm16
+    return lb
 
 
 # ------------------------------------------------------------------------------------ main
+def _speaker(item: dict) -> str:
+    return str(item.get("speaker", item.get("speaker_id", "default")))
+
+
 def run(cfg: dict) -> Optional[Dict[str, float]]:
     import torch.distributed as dist
 
+    from . import host_io
     from .extractor import SupDataExtractor
 
+    t_start = time.perf_counter()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # writer processes are forked before this process creates its CUDA context
-    writer = ParallelCacheWriter(int(cfg.get("writer_processes") or min(16, (os.cpu_count() or 1) // max(1, world))))
     torch.cuda.set_device(local_rank)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -411,71 +422,155 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
     if rank == 0:
         print(f"Processing {cfg['manifest_filepath']}:")
 
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_rank = max(1, cores // max(1, world))
+    decode_threads = max(1, min(int(cfg.get("dataloader_params", {}).get("num_workers", 16) or 1), per_rank))
+    writer_threads = int(cfg.get("writer_threads") or min(16, per_rank))
+
     durs = [it.get("duration") or os.path.getsize(it["audio_filepath"]) for it in items]
     mine = shard_indices(durs, world, rank)
-    speakers = sorted({str(it.get("speaker", it.get("speaker_id", "default"))) for it in items})
+    speakers = sorted({_speaker(it) for it in items})
     spk_index = {s: i + 1 for i, s in enumerate(speakers)}      # group 0 = "default" (all)
-    stats = empty_partials(len(speakers) + 1)
+    n_groups = len(speakers) + 1
+    stats = empty_partials(n_groups)                            # utterances whose pitch was already cached
+    acc = ex.new_pitch_partials(n_groups)                       # newly computed, accumulated on the device
 
+    # which cache files exist: one directory listing per type instead of five stat() calls per utterance
+    existing = {t: set(os.listdir(f)) if f.is_dir() else set() for t, f in folders.items()}
     todo, todo_ids = [], []
-    pitch_types = [t for t in ("pitch", "voiced_mask", "p_voiced") if t in types]
     for i in mine:
         it = items[i]
         uid = rel_audio_id(it["audio_filepath"], base_dir)
-        missing = [t for t in folders if not (folders[t] / f"{uid}.pt").exists()]
-        if missing or "align_prior_matrix" in types and not folders:
+        missing = [t for t in folders if f"{uid}.pt" not in existing[t]]
+        mel_path = it.get("mel_filepath")
+        if "log_mel" in missing and mel_path is not None and Path(mel_path).exists():
+            missing.remove("log_mel")                           # dataset.py:646-649: the manifest's own mel file wins
+        if missing:
             todo.append(i)
             todo_ids.append((uid, set(missing)))
         if "pitch" in folders and "pitch" not in missing:
             # already cached: its pitch still counts in the corpus statistics (the reference loads it)
             p = torch.load(folders["pitch"] / f"{uid}.pt").float().numpy()
             part = torch.from_numpy(partials_from_pitch(p))
-            g = spk_index[str(it.get("speaker", it.get("speaker_id", "default")))]
+            g = spk_index[_speaker(it)]
             stats[0] = merge_partials(stats[0], part)
             stats[g] = merge_partials(stats[g], part)
 
-    wavs = {}
+    sr = scfg.sample_rate
+    # batch composition from the manifest (duration, else file size): exact lengths come from the wav headers
+    approx = np.array([int(items[i]["duration"] * sr) if items[i].get("duration") else
+                       os.path.getsize(items[i]["audio_filepath"]) // 2 for i in todo], dtype=np.int64)
+    batches = make_batches(approx, int(float(cfg.get("batch_audio_seconds", 12000.0)) * sr)) if len(todo) else []
+    depth = max(2, int(cfg.get("pipeline_depth", 3)))
+    slots = [StagingSlot() for _ in range(depth)]
+    pitch_types = {"pitch", "voiced_mask", "p_voiced"}
+    spec_pad = scfg.n_fft // 2
 
-    def get_wav(i):
-        if i not in wavs:
-            wavs[i] = load_wav(items[i]["audio_filepath"], scfg.sample_rate)
-        return wavs[i]
+    def prefetch(bi: int) -> LoadedBatch:
+        slot = slots[bi % depth]
+        slot.free.wait()
+        slot.free.clear()
+        idx = [todo[k] for k in batches[bi]]
+        lb = load_batch(slot, [items[i]["audio_filepath"] for i in idx], sr, decode_threads)
+        lb.idx = idx
+        return lb
 
-    lengths = np.array([len(get_wav(i)) for i in todo], dtype=np.int64) if todo else np.zeros(0, np.int64)
-    for b in make_batches(lengths, int(float(cfg.get("batch_audio_seconds", 4000.0)) * scfg.sample_rate)):
-        idx = [todo[k] for k in b]
-        batch = ex.pack([get_wav(i) for i in idx])
-        if trim_kw is not None:
-            batch = ex.trim(batch, **trim_kw)
-        need = set().union(*[todo_ids[k][1] for k in b])
-        want = [t for t in types if t in need or t == "align_prior_matrix"]
-        if pitch_types and need & set(pitch_types):
-            want = list(set(want) | {"pitch", "voiced_mask", "p_voiced"})
-        tl = [text_length(items[i]) for i in idx]
-        groups = np.array([spk_index[str(items[i].get("speaker", items[i].get("speaker_id", "default")))] for i in idx],
-                          dtype=np.int32)
-        out = ex.extract(batch, text_lens=tl, types=want)
-        if "pitch" in out and out["pitch"] is not None:
-            newly = np.array(["pitch" in todo_ids[k][1] or "pitch" not in folders for k in b])
-            gp = ex.pitch_partials_grouped(out["pitch"], out["pitch_frame_off"], np.where(newly, groups, -1),
-                                           len(speakers) + 1).cpu()
-            stats = merge_partials(stats, gp)
-            gp0 = ex.pitch_partials_grouped(out["pitch"], out["pitch_frame_off"], np.where(newly, 0, -1), 1).cpu()
-            stats[0] = merge_partials(stats[0], gp0[0])
-        host = {k: out[k].cpu() for k in SUP_TYPES_ON_DISK if k in out and out[k] is not None and k in folders}
-        fo = out.get("frame_off")
-        pfo = out.get("pitch_frame_off")
-        jobs = []
-        for n, k in enumerate(b):
-            uid, missing = todo_ids[k]
-            for t in missing:
-                off = fo if t in ("log_mel", "energy") else pfo
-                jobs.append((t, int(off[n]), int(off[n + 1]), str(folders[t] / f"{uid}.pt")))
-        writer.submit_batch(host, jobs, scfg.n_mels)
-        for i in idx:
-            wavs.pop(i, None)
-    writer.close()
+    write_q: "queue.Queue" = queue.Queue()
+    write_err: List[BaseException] = []
 
+    def writer_loop():
+        while True:
+            job = write_q.get()
+            if job is None:
+                return
+            slot, ev, base, offs, shapes, paths, keep = job
+            try:
+                ev.synchronize()
+                del keep
+                if not write_err:
+                    host_io.pt_write_batch(base, offs, shapes, paths, writer_threads)
+            except BaseException as e:      # surfaced by the main thread
+                write_err.append(e)
+            finally:
+                slot.free.set()
+
+    wt = threading.Thread(target=writer_loop, daemon=True)
+    wt.start()
+    # three streams: H2D of batch b+1 and D2H of batch b-1 overlap the kernels of batch b
+    main_stream = torch.cuda.current_stream()
+    in_stream, out_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    loader = ThreadPoolExecutor(max_workers=1)
+    audio_seconds = 0.0
+    n_done = 0
+    t_stream = time.perf_counter()
+    try:
+        fut = loader.submit(prefetch, 0) if batches else None
+        for bi, b in enumerate(batches):
+            lb = fut.result()
+            fut = loader.submit(prefetch, bi + 1) if bi + 1 < len(batches) else None
+            if write_err:
+                raise write_err[0]
+            need = set().union(*[todo_ids[k][1] for k in b])
+            want = [t for t in SUP_TYPES_ON_DISK if t in need]
+            if need & pitch_types:
+                want = sorted(set(want) | pitch_types)
+            if {"log_mel", "energy"} & set(want) and int(lb.lens.min()) <= spec_pad:
+                k = int(np.argmin(lb.lens))
+                raise ValueError(f"{items[lb.idx[k]]['audio_filepath']}: {int(lb.lens[k])} samples, not longer than the "
+                                 f"STFT reflect padding ({spec_pad}); torch.stft rejects it in the reference too")
+            with torch.cuda.stream(in_stream):
+                raw = lb.host[:lb.total].to(ex.device, non_blocking=True)
+            main_stream.wait_stream(in_stream)
+            raw.record_stream(main_stream)
+            batch = ex.batch_from_device(ex.pcm16_to_f32(raw) if lb.pcm16 else raw, lb.offs, lb.lens)
+            if trim_kw is not None:
+                batch = ex.trim(batch, **trim_kw)
+            out = ex.extract(batch, types=want)
+            if out.get("pitch") is not None:
+                groups = np.array([spk_index[_speaker(items[i])] for i in lb.idx], dtype=np.int32)
+                newly = np.array(["pitch" in todo_ids[k][1] or "pitch" not in folders for k in b])
+                ex.pitch_partials_grouped(out["pitch"], out["pitch_frame_off"], np.where(newly, groups, -1), n_groups, acc)
+                ex.pitch_partials_grouped(out["pitch"], out["pitch_frame_off"], np.where(newly, 0, -1), n_groups, acc)
+            # D2H of every tensor this batch writes into ONE pinned buffer, then the native writer
+            fo, pfo = out.get("frame_off"), out.get("pitch_frame_off")
+            seg, pos = {}, 0
+            for t in want:
+                if t in folders and out.get(t) is not None:
+                    seg[t] = pos
+                    pos += out[t].numel()
+            hostbuf = lb.slot.buf("out", pos, torch.float32)
+            out_stream.wait_stream(main_stream)
+            with torch.cuda.stream(out_stream):
+                for t, o in seg.items():
+                    hostbuf[o:o + out[t].numel()].copy_(out[t], non_blocking=True)
+                    out[t].record_stream(out_stream)
+                ev = torch.cuda.Event()
+                ev.record(out_stream)
+            offs, shapes, paths = [], [], []
+            for n, k in enumerate(b):
+                uid, missing = todo_ids[k]
+                for t in missing:
+                    if t not in seg:
+                        continue
+                    off = fo if t in ("log_mel", "energy") else pfo
+                    a, e = int(off[n]), int(off[n + 1])
+                    if t == "log_mel":
+                        offs.append(seg[t] + scfg.n_mels * a); shapes.append((1, scfg.n_mels, e - a))
+                    else:
+                        offs.append(seg[t] + a); shapes.append((e - a,))
+                    paths.append(str(folders[t] / f"{uid}.pt"))
+            write_q.put((lb.slot, ev, hostbuf, np.array(offs, dtype=np.int64), shapes, paths, (out, batch)))
+            audio_seconds += float(batch.lens_host.sum()) / sr
+            n_done += len(b)
+    finally:
+        write_q.put(None)
+        wt.join()
+        loader.shutdown(wait=True)
+    if write_err:
+        raise write_err[0]
+    stream_seconds = time.perf_counter() - t_stream      # first decode submitted -> last cache file renamed
+
+    stats = merge_partials(stats, acc.cpu())
     stats = allreduce_partials(stats.cuda()).cpu() if world > 1 else stats
     result = stats_from_partials(stats[0])
     if rank == 0:
@@ -493,6 +588,11 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
             json.dump(table, f, indent=2)
     if world > 1:
         dist.barrier()
+    if result is not None:
+        result = dict(result)
+        result["run"] = {"utterances": n_done, "audio_seconds": audio_seconds, "seconds": time.perf_counter() - t_start,
+                         "stream_seconds": stream_seconds,
+                         "decode_threads": decode_threads, "writer_threads": writer_threads, "batches": len(batches)}
     return result
 
 

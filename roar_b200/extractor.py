@@ -42,6 +42,15 @@ def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+def _h2d(a: np.ndarray, dtype, device) -> torch.Tensor:
+    """Small index arrays (offsets, lengths, groups) host -> device through pinned memory, so the copy is
+    asynchronous on the current stream and the launching thread never waits for earlier kernels."""
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+    if t.numel() == 0:
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 def pack_layout(lens: np.ndarray, align: int = ALIGN):
     lens = np.asarray(lens, dtype=np.int64)
     padded = (lens + align - 1) // align * align
@@ -112,10 +121,7 @@ class SupDataExtractor:
 
     def pack_from_host_buffer(self, host: torch.Tensor, offs: np.ndarray, lens: np.ndarray) -> PackedBatch:
         audio = host.to(self.device, non_blocking=True)
-        return PackedBatch(audio,
-                           torch.from_numpy(np.ascontiguousarray(offs, dtype=np.int64)).to(self.device, non_blocking=True),
-                           torch.from_numpy(np.ascontiguousarray(lens, dtype=np.int32)).to(self.device, non_blocking=True),
-                           np.asarray(lens, dtype=np.int64), np.asarray(offs, dtype=np.int64))
+        return self.batch_from_device(audio, offs, lens)
 
     def pcm16_to_f32(self, pcm: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Device int16 PCM -> float32 ``x / 2**15`` (``segment.py:140-153``), on the current stream."""
@@ -131,16 +137,11 @@ class SupDataExtractor:
         sample, the integer -> float step of the wav decoder runs on the GPU."""
         assert host.dtype == torch.int16
         audio = self.pcm16_to_f32(host.to(self.device, non_blocking=True))
-        return PackedBatch(audio,
-                           torch.from_numpy(np.ascontiguousarray(offs, dtype=np.int64)).to(self.device, non_blocking=True),
-                           torch.from_numpy(np.ascontiguousarray(lens, dtype=np.int32)).to(self.device, non_blocking=True),
-                           np.asarray(lens, dtype=np.int64), np.asarray(offs, dtype=np.int64))
+        return self.batch_from_device(audio, offs, lens)
 
     def batch_from_device(self, audio: torch.Tensor, offs: np.ndarray, lens: np.ndarray) -> PackedBatch:
         assert audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous()
-        return PackedBatch(audio,
-                           torch.from_numpy(np.ascontiguousarray(offs, dtype=np.int64)).to(self.device),
-                           torch.from_numpy(np.ascontiguousarray(lens, dtype=np.int32)).to(self.device),
+        return PackedBatch(audio, _h2d(offs, np.int64, self.device), _h2d(lens, np.int32, self.device),
                            np.asarray(lens, dtype=np.int64), np.asarray(offs, dtype=np.int64))
 
     def trim(self, batch: PackedBatch, top_db: float = 60.0, ref: Optional[float] = None, frame_length: int = 2048,
@@ -172,7 +173,7 @@ class SupDataExtractor:
     def _frame_off(self, T: np.ndarray) -> (torch.Tensor, np.ndarray):
         fo = np.zeros(len(T) + 1, dtype=np.int64)
         np.cumsum(T, out=fo[1:])
-        return torch.from_numpy(fo).to(self.device, non_blocking=True), fo
+        return _h2d(fo, np.int64, self.device), fo
 
     def _workspace(self, n_utts: int, total_samples: int, frames: int, extra: int = 0) -> torch.Tensor:
         need = int(self.lib.roar_sup_workspace_bytes(self._h, n_utts, total_samples, frames)) + int(extra)
@@ -237,9 +238,9 @@ class SupDataExtractor:
         oo = np.zeros(len(tl) + 1, dtype=np.int64)
         np.cumsum(tl.astype(np.int64) * ml.astype(np.int64), out=oo[1:])
         out = torch.empty(int(oo[-1]), dtype=torch.float32, device=self.device)
-        d_tl = torch.from_numpy(tl).to(self.device, non_blocking=True)
-        d_ml = torch.from_numpy(ml).to(self.device, non_blocking=True)
-        d_oo = torch.from_numpy(oo).to(self.device, non_blocking=True)
+        d_tl = _h2d(tl, np.int32, self.device)
+        d_ml = _h2d(ml, np.int32, self.device)
+        d_oo = _h2d(oo, np.int64, self.device)
         _lib.check(self.lib.roar_sup_align_prior(self._h, _ptr(d_tl), _ptr(d_ml), len(tl), _ptr(d_oo),
                                                  int(ml.max()) if len(ml) else 0, float(scaling_factor),
                                                  _ptr(out), self._stream()))
@@ -254,9 +255,9 @@ class SupDataExtractor:
         oo = np.zeros(len(tl) + 1, dtype=np.int64)
         np.cumsum(tl.astype(np.int64) * ml.astype(np.int64), out=oo[1:])
         out = torch.empty(int(oo[-1]), dtype=torch.float32, device=self.device)
-        d_tl = torch.from_numpy(tl).to(self.device, non_blocking=True)
-        d_ml = torch.from_numpy(ml).to(self.device, non_blocking=True)
-        d_oo = torch.from_numpy(oo).to(self.device, non_blocking=True)
+        d_tl = _h2d(tl, np.int32, self.device)
+        d_ml = _h2d(ml, np.int32, self.device)
+        d_oo = _h2d(oo, np.int64, self.device)
         _lib.check(self.lib.roar_sup_align_prior_interp(self._h, _ptr(d_tl), _ptr(d_ml), len(tl), _ptr(d_oo),
                                                         int(ml.max()) if len(ml) else 0, int(round_mel_len_to),
                                                         int(round_text_len_to), _ptr(out), self._stream()))
@@ -281,8 +282,8 @@ class SupDataExtractor:
                                out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if out is None:
             out = self.new_pitch_partials(n_groups)
-        d_fo = torch.from_numpy(np.ascontiguousarray(frame_off, dtype=np.int64)).to(self.device)
-        d_g = torch.from_numpy(np.ascontiguousarray(groups, dtype=np.int32)).to(self.device)
+        d_fo = _h2d(frame_off, np.int64, self.device)
+        d_g = _h2d(groups, np.int32, self.device)
         _lib.check(self.lib.roar_sup_pitch_partials_grouped(self._h, _ptr(f0), _ptr(d_fo), _ptr(d_g), len(groups),
                                                             n_groups, _ptr(out), self._stream()))
         self.kernel_launches += 1

@@ -219,3 +219,119 @@ def synth_corpus_device(name: str, device, n_utts: Optional[int] = None, align: 
             audio[offs[i] : offs[i] + lens[i]] = y[b, : lens[i]]
     return (man, audio, torch.as_tensor(offs, device=device),
             torch.as_tensor(lens.astype(np.int32), device=device))
+
+
+# ------------------------------------------------------------------------------------------------------
+# Stateless device synthesis: utterance i of a corpus is a pure function of (corpus seed, utt_id), whatever
+# subset / batch it is generated in -- so every rank of a sharded run (bench.py --workload C3, SURVEY.md
+# section 8e) regenerates exactly its own utterances of ONE seeded manifest and the all-reduced pitch
+# statistics do not depend on the number of GPUs.  Per-utterance scalars come from a NumPy generator seeded by
+# (seed, 0xB0, utt_id); per-sample noise from a counter-based integer hash of (utt_id, stream, sample index).
+def _mix32(x):
+    """32-bit integer finaliser on int64 tensors holding uint32 values."""
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+    return x ^ (x >> 16)
+
+
+def _hash_normal(torch, utt_key, stream: int, L: int, device):
+    """Standard-normal float32 ``[B, L]``: Box-Muller over two hashed uniforms per sample."""
+    t = torch.arange(L, device=device, dtype=torch.int64)[None, :]
+    k = _mix32((utt_key[:, None] + stream * 0x9E3779B1) & 0xFFFFFFFF)
+    h1 = _mix32(k ^ _mix32(2 * t))
+    h2 = _mix32(k ^ _mix32(2 * t + 1))
+    u1 = (h1.to(torch.float32) + 0.5) * (1.0 / 4294967296.0)
+    u2 = (h2.to(torch.float32) + 0.5) * (1.0 / 4294967296.0)
+    return torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(6.283185307179586 * u2)
+
+
+def utterance_params(seed: int, utt_id: int) -> np.ndarray:
+    """The 64 per-utterance uniforms of the stateless generator."""
+    return np.random.default_rng([seed, 0xB0, utt_id]).random(64)
+
+
+def synth_corpus_device_stateless(name: str, device, indices=None, n_utts: Optional[int] = None, align: int = 4,
+                                  batch: int = 256, pcm16: bool = True):
+    """Packed ragged corpus on ``device`` for utterances ``indices`` (default: all) of manifest ``name``.
+
+    -> (manifest subset, audio float32 ``[total]``, sample_off int64 ``[n]``, sample_len int32 ``[n]``).  With
+    ``pcm16`` the samples are the exact ``x / 2**15`` values of a 16-bit quantisation (what a wav corpus holds:
+    ``audio * 32768`` is then integral and can travel host -> device as int16).  Same signal model as
+    ``synth_utterance``."""
+    import torch
+
+    spec = CORPORA[name]
+    sr = spec["sr"]
+    full = corpus_manifest(name, n_utts)
+    man = full if indices is None else [full[int(i)] for i in indices]
+    n = len(man)
+    lens = np.array([u.n_samples for u in man], dtype=np.int64)
+    padded = (lens + align - 1) // align * align
+    offs = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        offs[1:] = np.cumsum(padded)[:-1]
+    total = int(padded.sum())
+    audio = torch.zeros(total, dtype=torch.float32, device=device)
+    fbar_spk = {}
+    order = np.argsort(-lens, kind="stable")
+    two_pi = 2 * np.pi
+    for s in range(0, n, batch):
+        idx = order[s: s + batch]
+        B = len(idx)
+        Lmax = int(lens[idx].max())
+        L = torch.as_tensor(lens[idx], device=device)
+        P = np.stack([utterance_params(spec["seed"], man[i].utt_id) for i in idx])          # [B, 64]
+        for i in idx:
+            sp = man[i].speaker
+            if sp not in fbar_spk:
+                fbar_spk[sp] = speaker_mean_f0(spec["seed"], sp)
+        fbar_h = np.array([fbar_spk[man[i].speaker] for i in idx])
+        col = lambda j, lo=0.0, hi=1.0: torch.as_tensor(lo + (hi - lo) * P[:, j], device=device)[:, None]  # noqa: E731
+        t = torch.arange(Lmax, device=device, dtype=torch.float64)[None, :] / sr
+        fbar = torch.as_tensor(fbar_h, device=device)[:, None]
+        st = 0.3 * torch.sin(two_pi * 5.0 * t + col(0, 0, two_pi))
+        for q in range(3):
+            st = st + col(1 + 3 * q, 0.3, 1.0) * torch.sin(two_pi * col(2 + 3 * q, 0.1, 0.6) * t + col(3 + 3 * q, 0, two_pi))
+        per, ph0, duty = col(10, 0.18, 0.55), col(11), col(12, 0.55, 0.8)
+        cyc = t / per + ph0
+        frac = cyc - torch.floor(cyc)
+        edge = 0.005 / per
+        gate = torch.clamp(frac / edge, 0, 1) * torch.clamp((duty - frac) / edge, 0, 1)
+        syl = torch.floor(cyc)
+        h = torch.frac(torch.sin(syl * 12.9898 + ph0 * 78.233) * 43758.5453).abs()
+        gate = gate * (0.5 + 0.5 * h)
+        octave = torch.where(h < 0.04, torch.where(h < 0.02, 12.0, -12.0), 0.0)
+        noise_gate = torch.where((frac > duty) & (h > 0.5), 0.02 + 0.13 * h, 0.0)
+        f0 = fbar * torch.pow(2.0, (st + octave) / 12.0)
+        phase = two_pi * torch.cumsum(f0, dim=1) / sr
+        f1, f2 = col(13, 400, 900), col(14, 1200, 2600)
+        kmax_h = np.minimum(40, np.floor(0.45 * sr / (fbar_h * 2.0 ** (4.0 / 12.0)))).astype(np.int64)
+        kmax = torch.as_tensor(kmax_h, device=device)[:, None]
+        y = torch.zeros(B, Lmax, device=device, dtype=torch.float32)
+        for k in range(1, max(2, int(kmax_h.max()) + 1)):
+            fk = k * fbar
+            amp = (1.0 / k) * (1.0 + 2.0 * torch.exp(-0.5 * ((fk - f1) / 150.0) ** 2)
+                               + 1.5 * torch.exp(-0.5 * ((fk - f2) / 250.0) ** 2))
+            if k > 1:      # harmonic k only below 0.45 * sr for this utterance's speaker
+                amp = torch.where(kmax >= k, amp, torch.zeros_like(amp))
+            y += (amp * torch.sin(k * phase + col(15 + (k % 45), 0, two_pi))).float()
+        y = y * gate.float()
+        valid = (torch.arange(Lmax, device=device)[None, :] < L[:, None])
+        y = y * valid
+        peak = y.abs().amax(dim=1, keepdim=True).clamp_min(1e-9)
+        y = y / peak
+        key = torch.as_tensor([(man[i].utt_id * 2654435761 + spec["seed"] * 40503) & 0xFFFFFFFF for i in idx],
+                              device=device, dtype=torch.int64)
+        nz = _hash_normal(torch, key, 1, Lmax, device)
+        nz[:, 1:] = 0.6 * nz[:, 1:] + 0.4 * nz[:, :-1]
+        y = y + noise_gate.float() * nz
+        peak = (y * valid).abs().amax(dim=1, keepdim=True).clamp_min(1e-9)
+        y = y * (col(61, 0.3, 0.9).float() / peak)
+        y = y + (10 ** (-50 / 20)) * _hash_normal(torch, key, 2, Lmax, device)
+        y = torch.clamp(y, -1.0, 1.0) * valid
+        if pcm16:
+            y = torch.clamp(torch.round(y * 32767.0), -32768, 32767) * (1.0 / 32768.0)
+        for b, i in enumerate(idx):
+            audio[offs[i]: offs[i] + lens[i]] = y[b, : lens[i]]
+    return (man, audio, torch.as_tensor(offs, device=device),
+            torch.as_tensor(lens.astype(np.int32), device=device))

@@ -51,6 +51,18 @@ def test_ids_base_dir_and_manifest(tmp_path):
     items = X.read_manifest(str(m), min_duration=0.1, max_duration=20.0)
     assert [Path_stem(i) for i in items] == ["u2"]
     assert X.text_length({"text": "hello"}) == 7 and X.text_length({"text_tokens": [1, 2, 3]}) == 3
+    # TTSDataset.filter_files (dataset.py:367-406): the ignore file lists full audio_filepath strings ...
+    import pickle
+    ig = tmp_path / "ignore.pkl"
+    with open(ig, "wb") as f:
+        pickle.dump([str(paths[1]), "u3"], f)          # a bare stem does NOT match
+    items = X.read_manifest(str(m), ignore_file=str(ig))
+    assert [Path_stem(i) for i in items] == ["u1", "u3"]
+    # ... several manifests are concatenated, and the duration filter is off unless EVERY entry has a duration
+    m2 = tmp_path / "m2.json"
+    m2.write_text(json.dumps({"audio_filepath": str(tmp_path / "spk3" / "u4.wav"), "text": "x"}) + "\n")
+    items = X.read_manifest([str(m), str(m2)], min_duration=0.1, max_duration=20.0)
+    assert [Path_stem(i) for i in items] == ["u1", "u2", "u3", "u4"]
 
 
 def Path_stem(item):
@@ -65,7 +77,13 @@ def test_sharding_partitions_and_balances():
         allidx = np.concatenate(shards)
         assert len(allidx) == len(durs) and len(set(allidx.tolist())) == len(durs)
         tot = np.array([durs[s].sum() for s in shards])
-        assert tot.max() / tot.min() < 1.02
+        # longest-processing-time greedy: every rank within one (short) utterance of the mean
+        assert tot.max() - tot.min() <= durs.min() + 1e-9 or tot.max() / tot.min() < 1.001
+        assert all(np.array_equal(s, np.sort(s)) for s in shards)
+    # a skewed corpus (one very long utterance) still balances as well as it can
+    skew = np.array([100.0] + [1.0] * 300)
+    tot = np.array([skew[X.shard_indices(skew, 4, r)].sum() for r in range(4)])
+    assert tot.max() == 100.0 and tot.min() == 100.0
     b = X.make_batches(np.array([10, 50, 20, 40, 30]), 60)
     assert sorted(np.concatenate(b).tolist()) == [0, 1, 2, 3, 4]
     assert all(sum([10, 50, 20, 40, 30][i] for i in g) <= 60 or len(g) == 1 for g in b)
@@ -148,8 +166,55 @@ def test_wav_decode_int16_and_float(tmp_path):
     a = X.load_wav(str(tmp_path / "f.wav"), 22050)
     b = X.load_wav(str(tmp_path / "i.wav"), 22050)
     assert a.dtype == np.float32 and np.array_equal(a, x) and np.abs(b - x).max() < 1e-4
+    assert np.array_equal(b, (x * 32767).astype(np.int16).astype(np.float32) / 32768)     # x / 2^15, exact
     with pytest.raises(ValueError):
         X.load_wav(str(tmp_path / "f.wav"), 16000)
+
+
+def test_native_wav_decoder_formats_offset_duration(tmp_path):
+    """roar_sup_wav_* against scipy's decoder and AudioSegment's scaling rules (segment.py:140-153, 218-224):
+    PCM 8/16/24/32, float 32/64, stereo (average / one channel), offset + duration, raw int16 for the GPU path."""
+    import struct
+    import torch
+    from scipy.io import wavfile
+    from roar_b200 import host_io as H
+    rng = np.random.default_rng(0)
+    y = (0.5 * rng.standard_normal(30001)).clip(-1, 1)
+    i16 = (y * 32767).astype(np.int16)
+    i32 = (y * 2147483000).astype(np.int32)
+    u8 = ((y * 127) + 128).astype(np.uint8)
+    st = np.stack([i16, (i16 // 2).astype(np.int16)], axis=1)
+    cases = {"f32": (y.astype(np.float32), y.astype(np.float32)),
+             "i16": (i16, i16.astype(np.float32) / 32768),
+             "i32": (i32, (i32.astype(np.float64) / 2 ** 31).astype(np.float32)),
+             "u8": (u8, (u8.astype(np.float32) - 128) / 128),
+             "f64": (y, y.astype(np.float32)),
+             "st": (st, (st.astype(np.float32) / 32768).mean(axis=1))}
+    for k, (data, ref) in cases.items():
+        wavfile.write(tmp_path / f"{k}.wav", 22050, data)
+        got, sr = H.load_wav(str(tmp_path / f"{k}.wav"))
+        assert sr == 22050 and got.dtype == np.float32 and np.array_equal(got, ref), k
+    got, _ = H.load_wav(str(tmp_path / "st.wav"), channel=1)
+    assert np.array_equal(got, st[:, 1].astype(np.float32) / 32768)
+    got, _ = H.load_wav(str(tmp_path / "i16.wav"), offset=0.5, duration=0.25)
+    assert np.array_equal(got, cases["i16"][1][11025:11025 + 5512])
+    i24 = (y[:1000] * 8388607).astype(np.int32)
+    raw = b"".join(struct.pack("<i", int(v))[:3] for v in i24)
+    hdr = (b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, 22050, 66150, 3, 24)
+           + b"data" + struct.pack("<I", len(raw)))
+    (tmp_path / "i24.wav").write_bytes(hdr + raw)
+    got, _ = H.load_wav(str(tmp_path / "i24.wav"))
+    assert np.array_equal(got, (i24.astype(np.float64) / 2 ** 23).astype(np.float32))
+    info = H.wav_probe([str(tmp_path / "i16.wav"), str(tmp_path / "f32.wav")])
+    assert H.is_pcm16_mono(info).tolist() == [True, False] and info["n_frames"].tolist() == [30001, 30001]
+    dst = torch.zeros(30001 + 8, dtype=torch.int16)
+    H.wav_read([str(tmp_path / "i16.wav")], info[:1], np.array([0]), info["n_frames"][:1], dst, np.array([8]))
+    assert np.array_equal(dst.numpy()[8:], i16) and not dst.numpy()[:8].any()
+    with pytest.raises(Exception, match="nope.wav"):
+        H.wav_probe([str(tmp_path / "nope.wav")])
+    (tmp_path / "junk.wav").write_bytes(b"not a wav file at all")
+    with pytest.raises(Exception, match="RIFF"):
+        H.wav_probe([str(tmp_path / "junk.wav")])
 
 
 def test_featurizer_paths_config_and_collate(tmp_path):
@@ -217,21 +282,32 @@ def test_pitch_normalisation_and_stats_selection(tmp_path):
         du.select_pitch_stats({})
 
 
-def test_parallel_cache_writer(tmp_path):
-    """Worker processes write exactly the tensors the reference saves: CPU float32, log_mel [1, n_mels, T]."""
+def test_native_pt_writer_matches_torch_save(tmp_path):
+    """roar_sup_pt_write_batch writes exactly the tensors the reference saves with torch.save: CPU float32,
+    log_mel [1, n_mels, T], compact storage; readable by torch.load (weights_only or not) and a valid zip."""
+    import zipfile
     import torch
-    from roar_b200.extract_sup_data import ParallelCacheWriter
-    n_mels, T = 4, [3, 5, 2]
+    from roar_b200 import host_io as H
+    n_mels, T = 4, [3, 5, 2, 70000]
     fo = np.concatenate([[0], np.cumsum(T)])
-    host = {"log_mel": torch.arange(n_mels * fo[-1], dtype=torch.float32), "pitch": torch.arange(fo[-1], dtype=torch.float32)}
-    jobs = [(k, int(fo[i]), int(fo[i + 1]), str(tmp_path / f"{k}_{i}.pt")) for i in range(3) for k in host]
-    for procs in (1, 3):
-        w = ParallelCacheWriter(procs)
-        w.submit_batch({k: v.clone() for k, v in host.items()}, jobs, n_mels)
-        w.close()
-        for i in range(3):
-            lm = torch.load(tmp_path / f"log_mel_{i}.pt")
-            assert lm.shape == (1, n_mels, T[i]) and lm.dtype == torch.float32
-            assert torch.equal(lm.flatten(), host["log_mel"][n_mels * fo[i]:n_mels * fo[i + 1]])
-            assert torch.equal(torch.load(tmp_path / f"pitch_{i}.pt"), host["pitch"][fo[i]:fo[i + 1]])
-            assert lm.untyped_storage().nbytes() == lm.numel() * 4      # compact storage, not the whole batch
+    base = torch.randn(int((n_mels + 1) * fo[-1]))
+    offs, shapes, paths = [], [], []
+    for i in range(len(T)):
+        offs.append(n_mels * fo[i]); shapes.append((1, n_mels, T[i])); paths.append(str(tmp_path / "log_mel" / f"u{i}.pt"))
+        offs.append(n_mels * fo[-1] + fo[i]); shapes.append((T[i],)); paths.append(str(tmp_path / "pitch" / f"u{i}.pt"))
+    (tmp_path / "log_mel").mkdir(); (tmp_path / "pitch").mkdir()
+    for threads in (1, 4):
+        H.pt_write_batch(base, np.array(offs), shapes, paths, threads)
+        for o, sh, p in zip(offs, shapes, paths):
+            for wo in (True, False):
+                t = torch.load(p, weights_only=wo)
+                assert t.dtype == torch.float32 and tuple(t.shape) == sh and not t.is_cuda and t.is_contiguous()
+                assert torch.equal(t.flatten(), base[o:o + t.numel()])
+                assert t.untyped_storage().nbytes() == t.numel() * 4      # compact storage, not the whole batch
+            assert zipfile.ZipFile(p).testzip() is None
+        assert not [f for f in os.listdir(tmp_path / "pitch") if ".tmp" in f]
+    # same payload as torch.save: identical tensors after a round trip through either writer
+    torch.save(base[:12].view(1, 4, 3).clone(), tmp_path / "ref.pt")
+    assert torch.equal(torch.load(tmp_path / "ref.pt"), torch.load(paths[0]))
+    with pytest.raises(Exception):
+        H.pt_write_batch(base, np.array([0]), [(3,)], [str(tmp_path / "missing_dir" / "x.pt")], 1)
