@@ -114,6 +114,12 @@ void roar_sup_destroy(roar_sup_handle* h);
 int  roar_sup_set_profiling(roar_sup_handle* h, int on);
 int  roar_sup_profile_read(roar_sup_handle* h, double* ms_out, int64_t* count_out, int reset);
 
+/* Diagnostic builds only (-DROAR_VIT_STATS): per-category step counts of the Viterbi kernel since the last
+ * reset, out[n] uint64 ([0] sparse steps, [1] dense steps, [2] unvoiced band scans, [3] voiced band scans,
+ * [4] unvoiced list walks, [5] voiced list walks, [6] candidate evaluations, [7] utterance-steps in uniform mode).
+ * The regular build returns zeros. */
+int  roar_sup_debug_counters(uint64_t* out, int32_t n, int reset);
+
 /* Frame counts. STFT: 1 + L/hop (center) -- TTSDataset.get_spec, dataset.py:524-530;
  * pYIN: 1 + L/pyin_hop -- librosa.pyin center=True. */
 int64_t roar_sup_num_frames(const roar_sup_handle* h, int64_t n_samples);
@@ -137,6 +143,11 @@ size_t roar_sup_workspace_bytes(const roar_sup_handle* h, int32_t n_utts, int64_
                                 int64_t total_pyin_frames);
 /* Bytes roar_fbank_forward / roar_fbank_backward need for a batch of B rows. */
 size_t roar_fbank_workspace_bytes(const roar_sup_handle* h, int32_t B);
+
+/* Small metadata (offsets, lengths, prefix sums) host -> device by a kernel that reads the page-locked host block
+ * directly, so it never queues behind large copies on the copy engine.  16-byte aligned pointers and size;
+ * falls back to cudaMemcpyAsync when the host block is not page-locked. */
+int roar_sup_upload(roar_sup_handle* h, const void* host_pinned, void* d_dst, size_t bytes, void* stream);
 
 /* 16-bit PCM ingest: replaces the integer -> float32 step of AudioSegment._convert_samples_to_float32
  * (asr/parts/preprocessing/segment.py:140-153): d_audio[i] = d_pcm[i] / 2^15, exact.  The packed-batch

@@ -35,7 +35,19 @@ def normalize_batch(x, seq_len, normalize_type):
             x_std[i] = x[i, :, : seq_len[i].item()].std()
         x_std += CONSTANT
         return (x - x_mean.view(-1, 1, 1)) / x_std.view(-1, 1, 1)
+    if isinstance(normalize_type, dict) and "fixed_mean" in normalize_type and "fixed_std" in normalize_type:
+        x_mean = torch.tensor(normalize_type["fixed_mean"], dtype=x.dtype)
+        x_std = torch.tensor(normalize_type["fixed_std"], dtype=x.dtype)
+        return (x - x_mean.view(x.shape[0], x.shape[1]).unsqueeze(2)) / x_std.view(x.shape[0], x.shape[1]).unsqueeze(2)
     return x
+
+
+def splice_frames(x, frame_splicing):
+    """features.py:83-95, verbatim semantics (the cat of x[:, :, :n] and x[:, :, n:] is x itself)."""
+    seq = [x]
+    for n in range(1, frame_splicing):
+        seq.append(torch.cat([x[:, :, :n], x[:, :, n:]], dim=2))
+    return torch.cat(seq, dim=1)
 
 
 class FilterbankFeaturesOracle:
@@ -43,7 +55,7 @@ class FilterbankFeaturesOracle:
                  normalize="per_feature", n_fft=None, preemph=0.97, nfilt=64, lowfreq=0,
                  highfreq=None, log=True, log_zero_guard_type="add", log_zero_guard_value=2 ** -24,
                  pad_to=16, exact_pad=False, pad_value=0, mag_power=2.0, use_grads=False,
-                 mel_norm="slaney"):
+                 mel_norm="slaney", frame_splicing=1, max_duration=16.7):
         self.win_length = n_window_size
         self.hop_length = n_window_stride
         self.n_fft = n_fft or 2 ** math.ceil(math.log2(self.win_length))
@@ -53,6 +65,7 @@ class FilterbankFeaturesOracle:
         fn = fns.get(window, None)
         self.window = fn(self.win_length, periodic=False) if fn else None
         self.exact_pad = exact_pad
+        self.frame_splicing = frame_splicing
         self.normalize = normalize
         self.log = log
         self.preemph = preemph
@@ -62,6 +75,9 @@ class FilterbankFeaturesOracle:
         self.use_grads = use_grads
         self.log_zero_guard_type = log_zero_guard_type
         self.log_zero_guard_value = log_zero_guard_value
+        max_length = self.get_seq_len(torch.tensor(max_duration * sample_rate, dtype=torch.float))
+        max_pad = pad_to - (max_length % pad_to) if (pad_to != "max" and pad_to > 0) else 0
+        self.max_length = max_length + max_pad
         highfreq = highfreq or sample_rate / 2
         self.fb = torch.tensor(
             mel_filterbank(sample_rate, self.n_fft, nfilt, lowfreq, highfreq, norm=mel_norm),
@@ -108,13 +124,17 @@ class FilterbankFeaturesOracle:
                 x = torch.log(torch.clamp(x, min=self._guard(x)))
             else:
                 raise ValueError("log_zero_guard_type was not understood")
+        if self.frame_splicing > 1:
+            x = splice_frames(x, self.frame_splicing)
         if self.normalize:
             x = normalize_batch(x, seq_len, normalize_type=self.normalize)
         max_len = x.size(-1)
         mask = torch.arange(max_len).repeat(x.size(0), 1) >= seq_len.unsqueeze(1)
         x = x.masked_fill(mask.unsqueeze(1), self.pad_value)
         pad_to = self.pad_to
-        if pad_to > 0:
+        if pad_to == "max":
+            x = torch.nn.functional.pad(x, (0, int(self.max_length) - x.size(-1)), value=self.pad_value)
+        elif pad_to > 0:
             pad_amt = x.size(-1) % pad_to
             if pad_amt != 0:
                 x = torch.nn.functional.pad(x, (0, pad_to - pad_amt), value=self.pad_value)

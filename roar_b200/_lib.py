@@ -6,7 +6,9 @@ import os
 from .config import RoarSupConfig
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libroar_sup.so")
+# ROAR_SUP_LIB selects another build of the same library (kernel A/B measurements, diagnostic builds); the
+# default is the in-tree libroar_sup.so next to this file
+LIB_PATH = os.environ.get("ROAR_SUP_LIB") or os.path.join(HERE, "libroar_sup.so")
 
 # every symbol include/roar_sup.h declares
 SYMBOLS = [
@@ -18,7 +20,8 @@ SYMBOLS = [
     "roar_sup_pitch_partials_grouped", "roar_fbank_out_frames", "roar_fbank_forward",
     "roar_sup_set_profiling", "roar_sup_profile_read", "roar_sup_trim", "roar_fbank_backward",
     "roar_fbank_workspace_bytes", "roar_sup_pcm16_to_f32",
-    "roar_sup_wav_probe_batch", "roar_sup_wav_read_batch", "roar_sup_pt_write_batch",
+    "roar_sup_wav_probe_batch", "roar_sup_wav_read_batch", "roar_sup_pt_write_batch", "roar_sup_debug_counters",
+    "roar_sup_upload",
 ]
 ABI_VERSION = 2
 N_KERNEL_IDS = 12      # ROAR_K_COUNT
@@ -77,6 +80,8 @@ def load():
     lib.roar_sup_wav_probe_batch.argtypes = [vp, i32, vp, i32]
     lib.roar_sup_wav_read_batch.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp, i32]
     lib.roar_sup_pt_write_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32]
+    lib.roar_sup_debug_counters.argtypes = [vp, i32, ctypes.c_int]
+    lib.roar_sup_upload.argtypes = [vp, vp, vp, ctypes.c_size_t, vp]
     lib.roar_sup_set_profiling.argtypes = [vp, ctypes.c_int]
     lib.roar_sup_profile_read.argtypes = [vp, vp, vp, ctypes.c_int]
     if lib.roar_sup_abi_version() != ABI_VERSION:

@@ -24,19 +24,24 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """``out`` / ``defines``: a variant build (``-DNAME[=V]`` flags) written elsewhere, selected at run time with
+    ``ROAR_SUP_LIB=<out>`` -- kernel A/B measurements and the instrumented Viterbi (``ROAR_VIT_STATS``)."""
+    if out is None and not force and not needs_build():
         return LIB_PATH
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH, os.path.join(CSRC, "roar_sup.cu")]
+    target = out or LIB_PATH
+    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", target, os.path.join(CSRC, "roar_sup.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libroar_sup.so")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=outs[0] if outs else None, defines=defs))

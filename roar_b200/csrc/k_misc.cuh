@@ -237,6 +237,14 @@ __global__ void __launch_bounds__(256) k_pcm16_to_f32(const int16_t* __restrict_
   for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)pcm[i] * sc;
 }
 
+// Small metadata upload (offsets, lengths, frame prefix sums): the SMs read the pinned host block directly
+// (unified addressing) and write it to HBM.  A few KB per call; unlike cudaMemcpyAsync it does not queue
+// behind the multi-hundred-MB audio copies on the host-to-device copy engine, so the kernels that need the
+// metadata are not held up by them.  Both pointers 16-byte aligned, n16 = number of 16-byte words.
+__global__ void __launch_bounds__(256) k_upload_small(const uint4* __restrict__ host_src, uint4* __restrict__ dst, int64_t n16) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = host_src[i];
+}
+
 // ------------------------------------------------------------------------------------ K5 stats
 // get_pitch_stats (scripts/dataset_processing/tts/extract_sup_data.py:8-13): mean / unbiased std /
 // min / max over pitch != 0.  Produces float64 partials (sum, sumsq, count, min, max) that the ranks

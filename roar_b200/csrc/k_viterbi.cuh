@@ -468,7 +468,14 @@ HD double vit3_lower_bound(const Vit3Step& c, const uint16_t* row_id, double lp_
   return lb;
 }
 
+constexpr int VIT_STATS_N = 16;
 #ifdef __CUDACC__
+#ifdef ROAR_VIT_STATS
+__device__ unsigned long long g_vit_stats[VIT_STATS_N];
+#define VIT_STAT(i, v) do { if (tid == 0) atomicAdd(&g_vit_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define VIT_STAT(i, v) do { } while (0)
+#endif
 // Warp reductions over NEGATIVE finite doubles with redux.sync: for negative values, larger value <=>
 // smaller (hi, lo) bit pattern as unsigned.  Every V of this HMM is < 0 (sums of logs of
 // probabilities), and the fillers are -1e308.
@@ -624,6 +631,14 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     bool live_v = false, live_u = false;
     double nv = VIT_NEG, nu = VIT_NEG;
     const bool sparse = lp_u >= p.lt0 + VIT_SPARSE_MARGIN;     // block-uniform
+    VIT_STAT(sparse ? 0 : 1, 1);
+    VIT_STAT(c.nu > VIT_LIST_MAX ? 2 : 4, 1);
+    VIT_STAT(c.nv > VIT_LIST_MAX ? 3 : 5, 1);
+    VIT_STAT(6, nc_cur);
+    VIT_STAT(7, prev_vmax <= p.uniform_vmax ? 1 : 0);
+    VIT_STAT(8, (!sparse && c.nu > VIT_LIST_MAX) ? 1 : 0);
+    VIT_STAT(9, (!sparse && c.nv > VIT_LIST_MAX) ? 1 : 0);
+    VIT_STAT(10, (sparse && c.nv > VIT_LIST_MAX) ? 1 : 0);
     if (sparse) {
       VitBest2 bu;
       bu.b = VIT_NEG; bu.a = 0x7fffffff;

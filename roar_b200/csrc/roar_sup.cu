@@ -373,6 +373,19 @@ int roar_sup_create(const roar_sup_config* cfg, int device, roar_sup_handle** ou
   return rc;
 }
 
+int roar_sup_debug_counters(uint64_t* out, int32_t n, int reset) {
+  if (!out || n <= 0) return fail(ROAR_ERR_INVALID_ARG, "bad argument");
+  unsigned long long host[VIT_STATS_N] = {0};
+#ifdef ROAR_VIT_STATS
+  CUDA_TRY(cudaMemcpyFromSymbol(host, g_vit_stats, sizeof(host)));
+  if (reset) { unsigned long long z[VIT_STATS_N] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_vit_stats, z, sizeof(z))); }
+#else
+  (void)reset;
+#endif
+  for (int i = 0; i < n; ++i) out[i] = i < VIT_STATS_N ? host[i] : 0;
+  return 0;
+}
+
 int roar_sup_set_profiling(roar_sup_handle* h, int on) {
   if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
   h->profiling = on ? 1 : 0;
@@ -630,6 +643,28 @@ int roar_sup_pcm16_to_f32(roar_sup_handle* h, const int16_t* d_pcm, int64_t n_sa
   const int64_t cap = (int64_t)h->sm_count * 16;
   if (nb > cap) nb = cap;
   LAUNCH(h, ROAR_K_PCM16, (cudaStream_t)stream, k_pcm16_to_f32<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(d_pcm, n_samples, d_audio));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Metadata upload by kernel (see k_upload_small): `host_pinned` is page-locked host memory (cudaHostAlloc /
+// cudaHostRegister; a PyTorch pinned tensor), read by the SMs through its device alias.
+int roar_sup_upload(roar_sup_handle* h, const void* host_pinned, void* d_dst, size_t bytes, void* stream) {
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
+  if (bytes == 0) return 0;
+  if (!host_pinned || !d_dst) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if ((bytes & 15) || ((uintptr_t)host_pinned & 15) || ((uintptr_t)d_dst & 15))
+    return fail(ROAR_ERR_INVALID_ARG, "roar_sup_upload needs 16-byte aligned pointers and size");
+  void* alias = nullptr;
+  if (cudaHostGetDevicePointer(&alias, const_cast<void*>(host_pinned), 0) != cudaSuccess) {
+    cudaGetLastError();      // not page-locked / not mapped: take the copy engine
+    CUDA_TRY(cudaMemcpyAsync(d_dst, host_pinned, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+  }
+  const int64_t n16 = (int64_t)(bytes >> 4);
+  int64_t nb = (n16 + 255) / 256;
+  if (nb > 64) nb = 64;
+  k_upload_small<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>((const uint4*)alias, (uint4*)d_dst, n16);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -463,16 +463,30 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
     batches = make_batches(approx, int(float(cfg.get("batch_audio_seconds", 12000.0)) * sr)) if len(todo) else []
     depth = max(2, int(cfg.get("pipeline_depth", 3)))
     slots = [StagingSlot() for _ in range(depth)]
+    if batches:
+        # pin the staging buffers up front (page-locking a few hundred MB takes longer than processing a batch):
+        # 16-bit input and the float32 outputs of the largest batch, plus headroom for rounded durations
+        big = max(int(approx[b].sum()) for b in batches)
+        n_big = max(len(b) for b in batches)
+        per_frame = sum((scfg.n_mels if t == "log_mel" else 1) for t in folders)
+        for sl in slots[:min(depth, len(batches))]:
+            sl.buf("pcm16", int(big * 1.02) + 4 * n_big + 4096, torch.int16)
+            sl.buf("out", (int(big * 1.02) // scfg.hop + 2 * n_big) * per_frame, torch.float32)
+    timers = {"load": 0.0, "write": 0.0, "wait_load": 0.0, "wait_slot": 0.0}
     pitch_types = {"pitch", "voiced_mask", "p_voiced"}
     spec_pad = scfg.n_fft // 2
 
     def prefetch(bi: int) -> LoadedBatch:
         slot = slots[bi % depth]
+        t0 = time.perf_counter()
         slot.free.wait()
         slot.free.clear()
+        t1 = time.perf_counter()
         idx = [todo[k] for k in batches[bi]]
         lb = load_batch(slot, [items[i]["audio_filepath"] for i in idx], sr, decode_threads)
         lb.idx = idx
+        timers["wait_slot"] += t1 - t0
+        timers["load"] += time.perf_counter() - t1
         return lb
 
     write_q: "queue.Queue" = queue.Queue()
@@ -488,7 +502,9 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
                 ev.synchronize()
                 del keep
                 if not write_err:
+                    t0 = time.perf_counter()
                     host_io.pt_write_batch(base, offs, shapes, paths, writer_threads)
+                    timers["write"] += time.perf_counter() - t0
             except BaseException as e:      # surfaced by the main thread
                 write_err.append(e)
             finally:
@@ -506,7 +522,9 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
     try:
         fut = loader.submit(prefetch, 0) if batches else None
         for bi, b in enumerate(batches):
+            t0 = time.perf_counter()
             lb = fut.result()
+            timers["wait_load"] += time.perf_counter() - t0
             fut = loader.submit(prefetch, bi + 1) if bi + 1 < len(batches) else None
             if write_err:
                 raise write_err[0]
@@ -591,7 +609,7 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
     if result is not None:
         result = dict(result)
         result["run"] = {"utterances": n_done, "audio_seconds": audio_seconds, "seconds": time.perf_counter() - t_start,
-                         "stream_seconds": stream_seconds,
+                         "stream_seconds": stream_seconds, "stage_seconds": {k: round(v, 4) for k, v in timers.items()},
                          "decode_threads": decode_threads, "writer_threads": writer_threads, "batches": len(batches)}
     return result
 

@@ -18,6 +18,7 @@ from . import _lib
 from .config import SupConfig
 
 ALIGN = 4  # samples; utterance starts on 16-byte boundaries enable the TMA bulk-copy path
+_H2D_MODE = os.environ.get("ROAR_SUP_H2D", "pinned")      # diagnostics: "pageable" / "pageable_async"
 
 
 @dataclass
@@ -42,13 +43,74 @@ def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
-def _h2d(a: np.ndarray, dtype, device) -> torch.Tensor:
-    """Small index arrays (offsets, lengths, groups) host -> device through pinned memory, so the copy is
-    asynchronous on the current stream and the launching thread never waits for earlier kernels."""
-    t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
-    if t.numel() == 0:
-        return t.to(device)
-    return t.pin_memory().to(device, non_blocking=True)
+_NP2TORCH = {np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32, np.dtype(np.float64): torch.float64,
+             np.dtype(np.float32): torch.float32}
+
+
+class MetaStager:
+    """Small index arrays (offsets, lengths, frame prefix sums, groups) host -> device without the copy engine.
+
+    A ``cudaMemcpyAsync`` of a few KB from pinned memory queues on the host-to-device copy engine behind whatever
+    large audio copy is in flight there (hundreds of MB, several ms), and the kernels that need the array wait with
+    it: measured, the streamed extraction was 25 % slower that way than with blocking pageable copies.  Here the
+    arrays are written into a pinned arena and fetched by a tiny kernel that reads the arena directly
+    (``roar_sup_upload``), in stream order, so the launching thread never blocks either.  The arena is a ring of
+    segments; a segment is reused only after the uploads issued from it have completed (one event per stream that
+    used it)."""
+
+    SEG, NSEG = 1 << 20, 8
+
+    def __init__(self, lib, handle, device):
+        self.lib, self.h, self.device = lib, handle, device
+        self.arena = torch.empty(self.SEG * self.NSEG, dtype=torch.uint8, pin_memory=True)
+        self.view = self.arena.numpy()
+        self.seg, self.off = 0, 0
+        self.events = [[] for _ in range(self.NSEG)]
+        self.streams = {}
+        self.big = []
+
+    def _leave_segment(self):
+        self.events[self.seg] = []
+        for st in self.streams.values():
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self.events[self.seg].append(ev)
+        self.streams = {}
+        self.seg = (self.seg + 1) % self.NSEG
+        self.off = 0
+        for ev in self.events[self.seg]:
+            ev.synchronize()
+        self.events[self.seg] = []
+
+    def upload(self, a: np.ndarray, dtype) -> torch.Tensor:
+        a = np.ascontiguousarray(a, dtype=dtype)
+        tdt = _NP2TORCH[a.dtype]
+        if a.size == 0:
+            return torch.empty(0, dtype=tdt, device=self.device)
+        nbytes = a.nbytes
+        padded = (nbytes + 15) & ~15
+        stream = torch.cuda.current_stream(self.device)
+        dst = torch.empty(padded, dtype=torch.uint8, device=self.device)
+        if padded > self.SEG:                      # oversize: its own pinned block, kept until the upload is done
+            host = torch.empty(padded, dtype=torch.uint8, pin_memory=True)
+            host.numpy()[:nbytes] = a.view(np.uint8).reshape(-1)
+            src_ptr = host.data_ptr()
+        else:
+            if self.off + padded > self.SEG:
+                self._leave_segment()
+            o = self.seg * self.SEG + self.off
+            self.view[o:o + nbytes] = a.view(np.uint8).reshape(-1)
+            src_ptr = self.arena.data_ptr() + o
+            self.off += padded
+            self.streams[stream.cuda_stream] = stream
+            host = None
+        _lib.check(self.lib.roar_sup_upload(self.h, ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst.data_ptr()), padded,
+                                            ctypes.c_void_p(stream.cuda_stream)))
+        if host is not None:
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self.big = [(e, t) for e, t in self.big if not e.query()] + [(ev, host)]
+        return dst[:nbytes].view(tdt)
 
 
 def pack_layout(lens: np.ndarray, align: int = ALIGN):
@@ -78,6 +140,7 @@ class SupDataExtractor:
         (self.min_period, self.max_period, self.n_pitch_bins, self.transition_width,
          self.pyin_hop, self.pyin_win, self.kmax, self.n_transition_rows) = [int(x) for x in geo]
         self._ws: Optional[torch.Tensor] = None
+        self._meta = MetaStager(self.lib, self._h, self.device)
         self.kernel_launches = 0  # launches of our kernels issued through this object
         self._side = None
         self._ws_side = None
@@ -89,6 +152,13 @@ class SupDataExtractor:
                 self._h = None
         except Exception:
             pass
+
+    def _up(self, a, dtype) -> torch.Tensor:
+        """Small index array -> device (see MetaStager); ``ROAR_SUP_H2D=pageable`` keeps the blocking copy."""
+        if _H2D_MODE == "pageable":
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(self.device)
+        self.kernel_launches += 1
+        return self._meta.upload(np.asarray(a), dtype)
 
     # ------------------------------------------------------------------ geometry
     def num_frames(self, n_samples):
@@ -141,7 +211,7 @@ class SupDataExtractor:
 
     def batch_from_device(self, audio: torch.Tensor, offs: np.ndarray, lens: np.ndarray) -> PackedBatch:
         assert audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous()
-        return PackedBatch(audio, _h2d(offs, np.int64, self.device), _h2d(lens, np.int32, self.device),
+        return PackedBatch(audio, self._up(offs, np.int64), self._up(lens, np.int32),
                            np.asarray(lens, dtype=np.int64), np.asarray(offs, dtype=np.int64))
 
     def trim(self, batch: PackedBatch, top_db: float = 60.0, ref: Optional[float] = None, frame_length: int = 2048,
@@ -173,7 +243,7 @@ class SupDataExtractor:
     def _frame_off(self, T: np.ndarray) -> (torch.Tensor, np.ndarray):
         fo = np.zeros(len(T) + 1, dtype=np.int64)
         np.cumsum(T, out=fo[1:])
-        return _h2d(fo, np.int64, self.device), fo
+        return self._up(fo, np.int64), fo
 
     def _workspace(self, n_utts: int, total_samples: int, frames: int, extra: int = 0) -> torch.Tensor:
         need = int(self.lib.roar_sup_workspace_bytes(self._h, n_utts, total_samples, frames)) + int(extra)
@@ -238,9 +308,9 @@ class SupDataExtractor:
         oo = np.zeros(len(tl) + 1, dtype=np.int64)
         np.cumsum(tl.astype(np.int64) * ml.astype(np.int64), out=oo[1:])
         out = torch.empty(int(oo[-1]), dtype=torch.float32, device=self.device)
-        d_tl = _h2d(tl, np.int32, self.device)
-        d_ml = _h2d(ml, np.int32, self.device)
-        d_oo = _h2d(oo, np.int64, self.device)
+        d_tl = self._up(tl, np.int32)
+        d_ml = self._up(ml, np.int32)
+        d_oo = self._up(oo, np.int64)
         _lib.check(self.lib.roar_sup_align_prior(self._h, _ptr(d_tl), _ptr(d_ml), len(tl), _ptr(d_oo),
                                                  int(ml.max()) if len(ml) else 0, float(scaling_factor),
                                                  _ptr(out), self._stream()))
@@ -255,9 +325,9 @@ class SupDataExtractor:
         oo = np.zeros(len(tl) + 1, dtype=np.int64)
         np.cumsum(tl.astype(np.int64) * ml.astype(np.int64), out=oo[1:])
         out = torch.empty(int(oo[-1]), dtype=torch.float32, device=self.device)
-        d_tl = _h2d(tl, np.int32, self.device)
-        d_ml = _h2d(ml, np.int32, self.device)
-        d_oo = _h2d(oo, np.int64, self.device)
+        d_tl = self._up(tl, np.int32)
+        d_ml = self._up(ml, np.int32)
+        d_oo = self._up(oo, np.int64)
         _lib.check(self.lib.roar_sup_align_prior_interp(self._h, _ptr(d_tl), _ptr(d_ml), len(tl), _ptr(d_oo),
                                                         int(ml.max()) if len(ml) else 0, int(round_mel_len_to),
                                                         int(round_text_len_to), _ptr(out), self._stream()))
@@ -282,8 +352,8 @@ class SupDataExtractor:
                                out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if out is None:
             out = self.new_pitch_partials(n_groups)
-        d_fo = _h2d(frame_off, np.int64, self.device)
-        d_g = _h2d(groups, np.int32, self.device)
+        d_fo = self._up(frame_off, np.int64)
+        d_g = self._up(groups, np.int32)
         _lib.check(self.lib.roar_sup_pitch_partials_grouped(self._h, _ptr(f0), _ptr(d_fo), _ptr(d_g), len(groups),
                                                             n_groups, _ptr(out), self._stream()))
         self.kernel_launches += 1

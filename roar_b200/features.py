@@ -53,12 +53,14 @@ class FilterbankFeatures(nn.Module):
         if use_grads and (preemph is not None or normalize is not None):
             raise NotImplementedError("use_grads=True is differentiated for normalize=None, preemph=None (the "
                                       "reference's mel-loss configurations: jets.py:175-177, hifigan.py:56-58)")
-        if frame_splicing != 1:
-            raise NotImplementedError("frame_splicing > 1 is outside the accelerated path")
-        if isinstance(normalize, dict):
-            raise NotImplementedError("fixed_mean/fixed_std normalisation is outside the accelerated path")
-        if pad_to == "max":
-            raise NotImplementedError("pad_to='max' is outside the accelerated path")
+        if isinstance(normalize, dict) and not ("fixed_mean" in normalize and "fixed_std" in normalize):
+            raise ValueError("a normalize dict needs 'fixed_mean' and 'fixed_std' (features.py:50-57)")
+        if use_grads and (frame_splicing != 1 or pad_to == "max"):
+            raise NotImplementedError("use_grads=True is differentiated for frame_splicing=1 and an integer pad_to")
+        # Options the kernel does not fuse -- frame_splicing > 1, a fixed mean / std table, pad_to="max" -- run the
+        # kernel without normalisation / padding and finish with the reference's own tensor statements
+        # (features.py:434-460) on the device: they are shape plumbing, not arithmetic worth a kernel.
+        self._post = frame_splicing != 1 or isinstance(normalize, dict) or pad_to == "max"
         self.win_length = n_window_size
         self.hop_length = n_window_stride
         self.n_fft = n_fft or 2 ** math.ceil(math.log2(self.win_length))
@@ -84,8 +86,8 @@ class FilterbankFeatures(nn.Module):
             n_mels=nfilt, lowfreq=lowfreq, highfreq=highfreq or sample_rate / 2, mel_norm=mel_norm,
             spec_floor=CONSTANT if use_grads else 0.0, mag_power=mag_power, log_mode=(log_zero_guard_type if log else None),
             log_guard=guard, exact_pad=exact_pad, preemph=preemph,
-            normalize=normalize if normalize in ("per_feature", "all_features") else None,
-            pad_value=pad_value, pad_to=int(pad_to) if pad_to else 0,
+            normalize=normalize if normalize in ("per_feature", "all_features") and not self._post else None,
+            pad_value=pad_value, pad_to=int(pad_to) if pad_to and not self._post else 0,
             pyin=False)      # mel-only handle: no pYIN tables, none of pYIN's geometry limits
         self._c = self._cfg.to_c()
         self._lib = _lib.load()
@@ -99,7 +101,7 @@ class FilterbankFeatures(nn.Module):
         left = (self.n_fft - self.win_length) // 2
         self.register_buffer("window", torch.from_numpy(win[left:left + self.win_length].copy()))
         max_length = self.get_seq_len(torch.tensor(max_duration * sample_rate, dtype=torch.float))
-        max_pad = pad_to - (max_length % pad_to) if pad_to > 0 else 0
+        max_pad = pad_to - (max_length % pad_to) if (pad_to != "max" and pad_to > 0) else 0   # features.py:341-343
         self.max_length = max_length + max_pad
 
     def log_zero_guard_value_fn(self, x):
@@ -184,7 +186,36 @@ class FilterbankFeatures(nn.Module):
             out, out_len = _FbankFunction.apply(x, lens, self)
             return out, out_len
         with torch.no_grad():
-            return self._run_forward(x.contiguous().float(), lens)
+            out, out_len = self._run_forward(x.contiguous().float(), lens)
+            return (self._finish(out, out_len), out_len) if self._post else (out, out_len)
+
+    def _finish(self, x, seq_len):
+        """features.py:434-460 for the options the kernel leaves out.  ``x`` is the kernel's log-mel: valid frames
+        un-normalised, frames beyond ``seq_len`` already ``pad_value``, no padding of the time axis."""
+        if self.frame_splicing > 1:
+            # splice_frames (features.py:83-95): cat([x[:, :, :n], x[:, :, n:]], dim=2) is x itself, so the
+            # reference stacks `frame_splicing` copies of x along the feature axis
+            x = torch.cat([x] * self.frame_splicing, dim=1)
+        valid = (torch.arange(x.shape[2], device=x.device)[None, :] < seq_len[:, None]).unsqueeze(1)   # [B, 1, T]
+        if isinstance(self.normalize, dict):
+            mean = torch.tensor(self.normalize["fixed_mean"], device=x.device, dtype=x.dtype).view(x.shape[0], x.shape[1], 1)
+            std = torch.tensor(self.normalize["fixed_std"], device=x.device, dtype=x.dtype).view(x.shape[0], x.shape[1], 1)
+            x = (x - mean) / std
+        elif self.normalize in ("per_feature", "all_features"):
+            dims = (2,) if self.normalize == "per_feature" else (1, 2)
+            n = valid.sum(dim=dims, keepdim=True).to(x.dtype) * (1 if self.normalize == "per_feature" else x.shape[1])
+            xm = torch.where(valid, x, torch.zeros_like(x))
+            mean = xm.sum(dim=dims, keepdim=True) / n
+            var = (torch.where(valid, x - mean, torch.zeros_like(x)) ** 2).sum(dim=dims, keepdim=True) / (n - 1)
+            x = (x - mean) / (torch.sqrt(var) + CONSTANT)
+        x = x.masked_fill(~valid, self.pad_value)
+        if self.pad_to == "max":
+            x = nn.functional.pad(x, (0, int(self.max_length) - x.size(-1)), value=self.pad_value)
+        elif self.pad_to and self.pad_to > 0:
+            pad_amt = x.size(-1) % self.pad_to
+            if pad_amt != 0:
+                x = nn.functional.pad(x, (0, self.pad_to - pad_amt), value=self.pad_value)
+        return x
 
 
 class _FbankFunction(torch.autograd.Function):

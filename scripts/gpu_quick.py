@@ -13,7 +13,7 @@ from roar_b200.config import SupConfig
 from roar_b200.extractor import SupDataExtractor
 
 NAMES = ["tile_offsets", "stft_mel", "pyin_cmnd", "pyin_probs", "len_sort", "viterbi", "backtrack", "prior",
-         "stats", "fbank_norm", "pyin_energy"]
+         "stats", "fbank_norm", "pyin_energy", "pcm16"]
 
 
 def main():
@@ -37,8 +37,8 @@ def main():
         out = ex.extract(b, text_lens=tl, stats=ex.new_pitch_partials())
         e1.record()
         torch.cuda.synchronize()
-        ms = (ctypes.c_double * 11)()
-        cnt = (ctypes.c_int64 * 11)()
+        ms = (ctypes.c_double * 12)()
+        cnt = (ctypes.c_int64 * 12)()
         ex.lib.roar_sup_profile_read(ex._h, ms, cnt, 1)
         tot = e0.elapsed_time(e1)
         print(json.dumps({"rep": rep, "total_ms": tot, "audio_s": secs, "x_realtime": secs / (tot / 1e3),

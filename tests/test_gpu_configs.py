@@ -410,3 +410,30 @@ def test_cli_streaming_cache_roundtrip_through_reference_collate(tmp_path, capsy
             else:
                 assert torch.equal(a, b), n          # audio, text, lens, prior, normalised pitch, voiced mask, speaker
     REPORT["cli_roundtrip"] = {"utterances": 7, "orders": list(RC.TYPE_TABLE["orders"]), "run": res["run"]}
+
+
+def test_fbank_frame_splicing_fixed_stats_pad_to_max():
+    """FilterbankFeatures options finished with the reference's tensor statements after the kernel
+    (features.py:434-460): frame_splicing > 1, a fixed mean / std table, pad_to="max"."""
+    from oracle import fbank as ofbank
+    from roar_b200.features import FilterbankFeatures
+    rng = np.random.default_rng(3)
+    B, L = 3, 12000
+    lens = np.array([12000, 7000, 9001])
+    x = (0.2 * rng.standard_normal((B, L))).astype(np.float32)
+    for i in range(B):
+        x[i, lens[i]:] = 0
+    base = dict(sample_rate=16000, n_window_size=400, n_window_stride=160, nfilt=16, n_fft=512)
+    fixed = {"fixed_mean": rng.standard_normal((B, 16)).tolist(), "fixed_std": (1 + rng.random((B, 16))).tolist()}
+    cases = [dict(frame_splicing=3, normalize="per_feature", pad_to=16),
+             dict(frame_splicing=2, normalize="all_features", pad_to="max", max_duration=1.0, pad_value=-2.0),
+             dict(normalize=fixed, pad_to=8),
+             dict(normalize=None, pad_to="max", max_duration=1.0)]
+    for kw in cases:
+        m = FilterbankFeatures(dither=0.0, **base, **kw).cuda().eval()
+        got, got_len = m(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda())
+        ref, ref_len = ofbank.FilterbankFeaturesOracle(**base, **kw).forward(x, lens)
+        assert tuple(got.shape) == ref.shape, (kw, tuple(got.shape), ref.shape)
+        assert np.array_equal(got_len.cpu().numpy(), ref_len)
+        err = _rel(got.cpu().numpy(), ref)
+        assert np.quantile(err, 0.999) <= 1e-4 and err.max() <= 2e-3, (kw, float(err.max()))
