@@ -67,6 +67,71 @@ def main():
     run(True, True)                                            # warm-up
     res = {"n_gpus": world, "per_rank_GBps": {"h2d_only": run(True, False), "d2h_only": run(False, True),
                                               "both_directions_sum": run(True, True)}}
+    # the pattern of the e2e leg: 3.79 GB in, 2.49 GB out per step -> bytes-weighted both-direction run
+    n_in_e2e, n_out_e2e = int(n_in * 0.6), int(n_out * 0.4)
+
+    def run_ratio():
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        main = torch.cuda.current_stream()
+        e0.record(main)
+        s_in.wait_event(e0); s_out.wait_event(e0)
+        for _ in range(rounds):
+            with torch.cuda.stream(s_in):
+                d_in[:n_in_e2e].copy_(h_in[:n_in_e2e], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out[:n_out_e2e].copy_(d_out[:n_out_e2e], non_blocking=True)
+        main.wait_stream(s_in); main.wait_stream(s_out)
+        end = torch.cuda.Event(enable_timing=True)
+        end.record(main)
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(end)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return rounds * (n_in_e2e + n_out_e2e) / (float(ms.item()) * 1e-3) / 1e9
+    res["per_rank_GBps"]["both_60_40_like_e2e"] = run_ratio()
+    # write-combined pinned memory as the H2D source (cudaHostAllocWriteCombined through the runtime)
+    try:
+        import ctypes
+        rt = None
+        with open("/proc/self/maps") as f:
+            for ln in f:
+                if "libcudart" in ln:
+                    rt = ctypes.CDLL(ln.split()[-1])
+                    break
+        if rt is not None:
+            ptr = ctypes.c_void_p()
+            rt.cudaHostAlloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, ctypes.c_uint]
+            rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+            if rt.cudaHostAlloc(ctypes.byref(ptr), n_in, 0x04) == 0:       # cudaHostAllocWriteCombined
+                ctypes.memset(ptr, 1, n_in)
+
+                def run_wc(do_out):
+                    barrier()
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    main = torch.cuda.current_stream()
+                    e0.record(main)
+                    s_in.wait_event(e0); s_out.wait_event(e0)
+                    for _ in range(rounds):
+                        rt.cudaMemcpyAsync(ctypes.c_void_p(d_in.data_ptr()), ptr, n_in, 1, ctypes.c_void_p(s_in.cuda_stream))
+                        if do_out:
+                            with torch.cuda.stream(s_out):
+                                h_out.copy_(d_out, non_blocking=True)
+                    main.wait_stream(s_in); main.wait_stream(s_out)
+                    end = torch.cuda.Event(enable_timing=True)
+                    end.record(main)
+                    torch.cuda.synchronize()
+                    ms = torch.tensor([e0.elapsed_time(end)], device=dev, dtype=torch.float64)
+                    if world > 1:
+                        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                    barrier()
+                    return rounds * (n_in + (n_out if do_out else 0)) / (float(ms.item()) * 1e-3) / 1e9
+                res["per_rank_GBps"]["h2d_only_write_combined_source"] = run_wc(False)
+                res["per_rank_GBps"]["both_directions_sum_write_combined_source"] = run_wc(True)
+                rt.cudaFreeHost(ptr)
+    except Exception as e:      # diagnostics only
+        res["write_combined_error"] = repr(e)
     res["aggregate_GBps"] = {k: v * world for k, v in res["per_rank_GBps"].items()}
     res["cpu_count"] = os.cpu_count()
     res["how"] = f"{rounds} rounds x 1 GiB per direction per rank, pinned host memory, max over ranks of the CUDA-event time"
