@@ -144,6 +144,16 @@ size_t roar_sup_workspace_bytes(const roar_sup_handle* h, int32_t n_utts, int64_
 /* Bytes roar_fbank_forward / roar_fbank_backward need for a batch of B rows. */
 size_t roar_fbank_workspace_bytes(const roar_sup_handle* h, int32_t B);
 
+/* Sample-rate conversion of a packed batch on the device: replaces the resampling step of AudioSegment.__init__
+ * (asr/parts/preprocessing/segment.py:68-75; the reference calls librosa.core.resample, res_type soxr_hq).
+ * Polyphase FIR with scipy.signal.resample_poly's arithmetic: out[n] = sum_k taps[(n + n_pre_remove) * down -
+ * n_pre_pad - k * up] * in[k]; the host designs `taps` (low-pass, multiplied by `up`) and the output lengths
+ * (roar_b200/resample.py).  A different filter than soxr's: parity unpinned (oracle/resample.py). */
+int roar_sup_resample(roar_sup_handle* h, const float* d_in, const int64_t* d_in_off, const int32_t* d_in_len,
+                      int32_t n_utts, int32_t max_out_len, int32_t up, int32_t down, const float* d_taps,
+                      int32_t n_taps, int32_t n_pre_pad, int32_t n_pre_remove, float* d_out,
+                      const int64_t* d_out_off, const int32_t* d_out_len, void* stream);
+
 /* Small metadata (offsets, lengths, prefix sums) host -> device by a kernel that reads the page-locked host block
  * directly, so it never queues behind large copies on the copy engine.  16-byte aligned pointers and size;
  * falls back to cudaMemcpyAsync when the host block is not page-locked. */

@@ -21,7 +21,7 @@ SYMBOLS = [
     "roar_sup_set_profiling", "roar_sup_profile_read", "roar_sup_trim", "roar_fbank_backward",
     "roar_fbank_workspace_bytes", "roar_sup_pcm16_to_f32",
     "roar_sup_wav_probe_batch", "roar_sup_wav_read_batch", "roar_sup_pt_write_batch", "roar_sup_debug_counters",
-    "roar_sup_upload",
+    "roar_sup_upload", "roar_sup_resample",
 ]
 ABI_VERSION = 2
 N_KERNEL_IDS = 12      # ROAR_K_COUNT
@@ -82,6 +82,7 @@ def load():
     lib.roar_sup_pt_write_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32]
     lib.roar_sup_debug_counters.argtypes = [vp, i32, ctypes.c_int]
     lib.roar_sup_upload.argtypes = [vp, vp, vp, ctypes.c_size_t, vp]
+    lib.roar_sup_resample.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.roar_sup_set_profiling.argtypes = [vp, ctypes.c_int]
     lib.roar_sup_profile_read.argtypes = [vp, vp, vp, ctypes.c_int]
     if lib.roar_sup_abi_version() != ABI_VERSION:

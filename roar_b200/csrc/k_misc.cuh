@@ -215,7 +215,46 @@ __global__ void __launch_bounds__(256) k_trim(const TrimParams p) {
 }
 #endif  // __CUDACC__
 
+// ------------------------------------------------------------------------------------ K8 polyphase resampler
+// Rational-rate FIR resampling of a packed batch: upsample by `up`, low-pass, downsample by `down`, with the
+// arithmetic of scipy.signal.resample_poly / upfirdn (zero extension at the ends):
+//   out[n] = sum_k taps[(n + n_pre_remove) * down - n_pre_pad - k * up] * x[k]
+// over the k whose tap index falls inside [0, n_taps).  `taps` is the host-built low-pass (Kaiser-windowed sinc,
+// already multiplied by `up`).  Replaces the resampling step of AudioSegment.__init__
+// (asr/parts/preprocessing/segment.py:68-75), where the reference calls librosa.core.resample (soxr_hq): a
+// different filter design of the same band limit -- parity unpinned, see oracle/resample.py.
+struct ResampleParams {
+  const float* in;
+  const int64_t* in_off;
+  const int32_t* in_len;
+  const int64_t* out_off;
+  const int32_t* out_len;
+  float* out;
+  const float* taps;
+  int32_t n_utts, n_taps, up, down, n_pre_pad, n_pre_remove;
+};
+HD float resample_one(const ResampleParams& p, const float* x, int L, int n) {
+  const int64_t c = ((int64_t)n + p.n_pre_remove) * p.down - p.n_pre_pad;
+  // k*up <= c  and  c - k*up <= n_taps - 1
+  int64_t k_hi = c >= 0 ? c / p.up : -1;
+  int64_t lo_num = c - (p.n_taps - 1);
+  int64_t k_lo = lo_num <= 0 ? 0 : (lo_num + p.up - 1) / p.up;
+  if (k_hi > L - 1) k_hi = L - 1;
+  double acc = 0.0;
+  for (int64_t k = k_lo; k <= k_hi; ++k) acc += (double)p.taps[c - k * p.up] * (double)x[k];
+  return (float)acc;
+}
+
 #ifdef __CUDACC__
+// grid.y = utterance, grid.x * blockDim.x covers the longest output
+__global__ void __launch_bounds__(256) k_resample(const ResampleParams p, int32_t utt_base) {
+  const int utt = utt_base + blockIdx.y;
+  const int n_out = p.out_len[utt], L = p.in_len[utt];
+  const float* x = p.in + p.in_off[utt];
+  float* y = p.out + p.out_off[utt];
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_out; n += gridDim.x * blockDim.x) y[n] = resample_one(p, x, L, n);
+}
+
 // ------------------------------------------------------------------------------------ K0 16-bit PCM ingest
 // int16 -> float32 / 2^15 (exact).  Grid-stride, 8 samples per thread per trip: one 16-byte load, two
 // 16-byte stores when both pointers are 16-byte aligned; scalar head/tail otherwise.

@@ -647,6 +647,26 @@ int roar_sup_pcm16_to_f32(roar_sup_handle* h, const int16_t* d_pcm, int64_t n_sa
   return 0;
 }
 
+int roar_sup_resample(roar_sup_handle* h, const float* d_in, const int64_t* d_in_off, const int32_t* d_in_len, int32_t n_utts,
+                      int32_t max_out_len, int32_t up, int32_t down, const float* d_taps, int32_t n_taps, int32_t n_pre_pad,
+                      int32_t n_pre_remove, float* d_out, const int64_t* d_out_off, const int32_t* d_out_len, void* stream) {
+  if (!h) return fail(ROAR_ERR_INVALID_ARG, "null handle");
+  if (n_utts <= 0 || max_out_len <= 0) return 0;
+  if (!d_in || !d_in_off || !d_in_len || !d_taps || !d_out || !d_out_off || !d_out_len) return fail(ROAR_ERR_INVALID_ARG, "null argument");
+  if (up < 1 || down < 1 || n_taps < 1) return fail(ROAR_ERR_INVALID_ARG, "resample: up, down and n_taps must be >= 1");
+  ResampleParams p;
+  p.in = d_in; p.in_off = d_in_off; p.in_len = d_in_len; p.out_off = d_out_off; p.out_len = d_out_len; p.out = d_out;
+  p.taps = d_taps; p.n_utts = n_utts; p.n_taps = n_taps; p.up = up; p.down = down; p.n_pre_pad = n_pre_pad; p.n_pre_remove = n_pre_remove;
+  unsigned gx = (unsigned)((max_out_len + 255) / 256);
+  if (gx > 1024) gx = 1024;
+  for (int32_t u0 = 0; u0 < n_utts; u0 += 65535) {
+    const unsigned gy = n_utts - u0 < 65535 ? n_utts - u0 : 65535;
+    k_resample<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(p, u0);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // Metadata upload by kernel (see k_upload_small): `host_pinned` is page-locked host memory (cudaHostAlloc /
 // cudaHostRegister; a PyTorch pinned tensor), read by the SMs through its device alias.
 int roar_sup_upload(roar_sup_handle* h, const void* host_pinned, void* d_dst, size_t bytes, void* stream) {

@@ -17,7 +17,9 @@ positionally); statistics are accumulated in float64 and a
 ranks; ``pitch_stats.json`` (``default`` + per speaker, the format ``pitch_stats_path`` reads,
 ``dataset.py:485-487, 720-733``) is written next to the cache.
 ``dataset.trim=true`` (+ ``trim_ref``, ``trim_top_db``, ``trim_frame_length``, ``trim_hop_length``) runs
-``librosa.effects.trim`` on the GPU (``roar_sup_trim``).
+``librosa.effects.trim`` on the GPU (``roar_sup_trim``); wav files at another sample rate are converted to
+``dataset.sample_rate`` on the GPU (``roar_sup_resample``, polyphase FIR -- the reference uses librosa's soxr_hq
+there, so resampled audio agrees only as two good low-pass designs do: roar_b200/resample.py).
 
 The run is a bounded-memory stream (the reference overlaps decode and compute through
 ``DataLoader(num_workers=...)``, ``extract_sup_data.py:66-71``):
@@ -47,6 +49,7 @@ import numpy as np
 import torch
 
 from .config import PITCH_FMAX_C7, PITCH_FMIN_C2, SupConfig
+from .dataset_utils import PackedCache, write_packed_batch
 
 SUP_TYPES_ON_DISK = ("log_mel", "pitch", "voiced_mask", "p_voiced", "energy")
 VALID_SUP_TYPES = SUP_TYPES_ON_DISK + ("align_prior_matrix", "speaker_id")
@@ -65,6 +68,11 @@ DEFAULTS = {
     "batch_audio_seconds": 12000.0,  # audio per device call (bounds the Viterbi scratch and the staging buffers)
     "pipeline_depth": 3,             # staging-buffer sets in flight: decode | compute | write
     "writer_threads": None,          # native .pt writer threads (default: min(16, cores))
+    # "pt" (default): one torch-loadable file per utterance and type, the layout TTSDataset reads;
+    # "packed": one raw float32 shard per batch and type + a JSON-lines index -- two
+    # sequential writes per batch instead of five small files per utterance; read back with
+    # roar_b200.dataset_utils.PackedCache (load(type, id) -> the tensor torch.load would have returned)
+    "cache_format": "pt",
 }
 
 
@@ -353,7 +361,7 @@ def _zero_gaps(hv: np.ndarray, offs: np.ndarray, lens: np.ndarray, total: int):
 
 
 class LoadedBatch:
-    __slots__ = ("slot", "idx", "host", "offs", "lens", "total", "pcm16")
+    __slots__ = ("slot", "idx", "host", "offs", "lens", "total", "pcm16", "srs")
 
 
 def load_batch(slot: StagingSlot, paths: List[str], sample_rate: int, threads: int) -> LoadedBatch:
@@ -362,10 +370,6 @@ def load_batch(slot: StagingSlot, paths: List[str], sample_rate: int, threads: i
     from . import host_io
     from .extractor import pack_layout
     info = host_io.wav_probe(paths, threads)
-    bad = np.flatnonzero(info["sample_rate"] != sample_rate)
-    if len(bad):
-        raise ValueError(f"{paths[int(bad[0])]}: sample rate {int(info['sample_rate'][bad[0]])} != dataset.sample_rate "
-                         f"{sample_rate}; resample the corpus first (roar_b200.resample)")
     lens = info["n_frames"].astype(np.int64)
     offs, total = pack_layout(lens)
     pcm16 = bool(host_io.is_pcm16_mono(info).all())
@@ -374,6 +378,8 @@ def load_batch(slot: StagingSlot, paths: List[str], sample_rate: int, threads: i
     _zero_gaps(host.numpy(), offs, lens, total)
     lb = LoadedBatch()
     lb.slot, lb.host, lb.offs, lb.lens, lb.total, lb.pcm16 = slot, host, offs, lens, total, pcm16
+    # files at another rate are resampled on the GPU (target_sr, segment.py:68-75)
+    lb.srs = None if bool((info["sample_rate"] == sample_rate).all()) else info["sample_rate"].astype(np.int64)
     return lb
 
 
@@ -387,6 +393,7 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
 
     from . import host_io
     from .extractor import SupDataExtractor
+    from .resample import resample_batch
 
     t_start = time.perf_counter()
     rank = int(os.environ.get("RANK", "0"))
@@ -491,6 +498,15 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
 
     write_q: "queue.Queue" = queue.Queue()
     write_err: List[BaseException] = []
+    packed = str(cfg.get("cache_format", "pt")).lower() == "packed"
+    packed_dir = (sup_path / "packed") if packed else None
+    packed_index: List[str] = []
+    run_id = f"{int(time.time()):x}"                           # shards of a resumed run never overwrite earlier ones
+    if packed:
+        packed_dir.mkdir(parents=True, exist_ok=True)
+        done = PackedCache.index_ids(packed_dir)              # utterances a previous packed run already holds
+        keep = [k for k, (uid, _) in enumerate(todo_ids) if uid not in done]
+        todo, todo_ids = [todo[k] for k in keep], [todo_ids[k] for k in keep]
 
     def writer_loop():
         while True:
@@ -503,7 +519,10 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
                 del keep
                 if not write_err:
                     t0 = time.perf_counter()
-                    host_io.pt_write_batch(base, offs, shapes, paths, writer_threads)
+                    if packed_dir is None:
+                        host_io.pt_write_batch(base, offs, shapes, paths, writer_threads)
+                    else:
+                        write_packed_batch(packed_dir, f"r{rank}_{run_id}_b{len(packed_index):06d}", base, offs, shapes, paths, packed_index)
                     timers["write"] += time.perf_counter() - t0
             except BaseException as e:      # surfaced by the main thread
                 write_err.append(e)
@@ -532,17 +551,19 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
             want = [t for t in SUP_TYPES_ON_DISK if t in need]
             if need & pitch_types:
                 want = sorted(set(want) | pitch_types)
-            if {"log_mel", "energy"} & set(want) and int(lb.lens.min()) <= spec_pad:
-                k = int(np.argmin(lb.lens))
-                raise ValueError(f"{items[lb.idx[k]]['audio_filepath']}: {int(lb.lens[k])} samples, not longer than the "
-                                 f"STFT reflect padding ({spec_pad}); torch.stft rejects it in the reference too")
             with torch.cuda.stream(in_stream):
                 raw = lb.host[:lb.total].to(ex.device, non_blocking=True)
             main_stream.wait_stream(in_stream)
             raw.record_stream(main_stream)
             batch = ex.batch_from_device(ex.pcm16_to_f32(raw) if lb.pcm16 else raw, lb.offs, lb.lens)
+            if lb.srs is not None:
+                batch = resample_batch(ex, batch, lb.srs, sr)
             if trim_kw is not None:
                 batch = ex.trim(batch, **trim_kw)
+            if {"log_mel", "energy"} & set(want) and int(batch.lens_host.min()) <= spec_pad:
+                k = int(np.argmin(batch.lens_host))
+                raise ValueError(f"{items[lb.idx[k]]['audio_filepath']}: {int(batch.lens_host[k])} samples, not longer "
+                                 f"than the STFT reflect padding ({spec_pad}); torch.stft rejects it in the reference too")
             out = ex.extract(batch, types=want)
             if out.get("pitch") is not None:
                 groups = np.array([spk_index[_speaker(items[i])] for i in lb.idx], dtype=np.int32)
@@ -576,7 +597,7 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
                         offs.append(seg[t] + scfg.n_mels * a); shapes.append((1, scfg.n_mels, e - a))
                     else:
                         offs.append(seg[t] + a); shapes.append((e - a,))
-                    paths.append(str(folders[t] / f"{uid}.pt"))
+                    paths.append(f"{t}/{uid}" if packed else str(folders[t] / f"{uid}.pt"))
             write_q.put((lb.slot, ev, hostbuf, np.array(offs, dtype=np.int64), shapes, paths, (out, batch)))
             audio_seconds += float(batch.lens_host.sum()) / sr
             n_done += len(b)
@@ -586,6 +607,9 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
         loader.shutdown(wait=True)
     if write_err:
         raise write_err[0]
+    if packed and packed_index:
+        with open(packed_dir / f"index_r{rank}.jsonl", "a", encoding="utf-8") as f:
+            f.write("".join(packed_index))
     stream_seconds = time.perf_counter() - t_stream      # first decode submitted -> last cache file renamed
 
     stats = merge_partials(stats, acc.cpu())

@@ -437,3 +437,82 @@ def test_fbank_frame_splicing_fixed_stats_pad_to_max():
         assert np.array_equal(got_len.cpu().numpy(), ref_len)
         err = _rel(got.cpu().numpy(), ref)
         assert np.quantile(err, 0.999) <= 1e-4 and err.max() <= 2e-3, (kw, float(err.max()))
+
+
+def test_resampler_vs_scipy_and_cli_mixed_rates(tmp_path, capsys):
+    """Row N3: roar_sup_resample against scipy.signal.resample_poly (the kernel's arithmetic; parity with the
+    reference's soxr_hq is unpinned, oracle/resample.py), a pass-band tone check, and the CLI on a corpus that mixes
+    22.05 kHz files with 44.1 kHz / 16 kHz ones (resampled on the GPU, then identical to feeding the resampled audio)."""
+    from scipy.io import wavfile
+    from oracle import pool, resample as oresample, spec as ospec
+    from roar_b200 import extract_sup_data as X, synth
+    from roar_b200.config import SupConfig
+    from roar_b200.extractor import SupDataExtractor
+    from roar_b200.resample import resample_batch
+    ex = SupDataExtractor(SupConfig(highfreq=8000.0))
+    rng = np.random.default_rng(4)
+    for a, b in ((44100, 22050), (48000, 22050), (16000, 22050), (22050, 16000)):
+        wavs = [(0.3 * rng.standard_normal(n)).astype(np.float32) for n in (1, 257, 10007, 44100)]
+        out = resample_batch(ex, ex.pack(wavs), a, b)
+        for i, w in enumerate(wavs):
+            ref = oresample.resample(w, a, b)
+            got = out.audio[int(out.offs_host[i]):int(out.offs_host[i] + out.lens_host[i])].cpu().numpy()
+            assert got.shape == ref.shape, (a, b, got.shape, ref.shape)
+            assert np.abs(got - ref).max() <= 2e-6, (a, b, float(np.abs(got - ref).max()))
+    t = np.arange(44100) / 44100.0
+    tone = (0.5 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
+    y = resample_batch(ex, ex.pack([tone]), 44100, 22050).audio.cpu().numpy()[:22050]
+    assert oresample.band_limited_check(y, 22050, 1000.0, 0.5)
+    # CLI: mixed sample rates in one manifest
+    rows, expect = [], []
+    for k, sr in enumerate((22050, 44100, 16000, 22050)):
+        yk = synth.synth_utterance(77, k, int(1.5 * sr) + 100 * k, sr, k)
+        p = tmp_path / "w" / f"u{k}.wav"
+        p.parent.mkdir(exist_ok=True)
+        wavfile.write(p, sr, pool.quantize_pcm16(yk))
+        y16 = pool.quantize_pcm16(yk).astype(np.float32) / np.float32(32768.0)
+        expect.append(y16 if sr == 22050 else oresample.resample(y16, sr, 22050))
+        rows.append(json.dumps({"audio_filepath": str(p), "duration": len(yk) / sr, "text": "abc"}))
+    mf = tmp_path / "m.json"
+    mf.write_text("\n".join(rows) + "\n")
+    sup = tmp_path / "sup"
+    X.main([f"manifest_filepath={mf}", f"sup_data_path={sup}", "sup_data_types=[log_mel,energy]"])
+    capsys.readouterr()
+    fb = ex.mel_filterbank()
+    for k, yk in enumerate(expect):
+        lm = torch.load(sup / "log_mel" / f"u{k}.pt").numpy()
+        ref = ospec.get_log_mel(yk, fb).numpy()
+        assert lm.shape == ref.shape, (k, lm.shape, ref.shape)
+        assert _rel(lm, ref).max() <= 2e-4, (k, float(_rel(lm, ref).max()))     # resampler rounding (2e-6 abs) on top of the 1e-4 gate
+
+
+def test_cli_packed_cache_equals_pt_cache(tmp_path, capsys):
+    """`cache_format=packed`: the packed shards + index hold exactly the tensors of the per-file layout."""
+    from scipy.io import wavfile
+    from oracle import pool
+    from roar_b200 import extract_sup_data as X, synth
+    from roar_b200.dataset_utils import PackedCache
+    rows = []
+    for k in range(5):
+        y = synth.synth_utterance(99, k, 22050 + 3000 * k, 22050, k)
+        p = tmp_path / "w" / f"u{k}.wav"
+        p.parent.mkdir(exist_ok=True)
+        wavfile.write(p, 22050, pool.quantize_pcm16(y))
+        rows.append(json.dumps({"audio_filepath": str(p), "duration": len(y) / 22050, "text": "abc"}))
+    mf = tmp_path / "m.json"
+    mf.write_text("\n".join(rows) + "\n")
+    types = "sup_data_types=[log_mel,pitch,voiced_mask,p_voiced,energy]"
+    a = X.main([f"manifest_filepath={mf}", f"sup_data_path={tmp_path / 'pt'}", types, "batch_audio_seconds=3"])
+    b = X.main([f"manifest_filepath={mf}", f"sup_data_path={tmp_path / 'pk'}", types, "batch_audio_seconds=3", "cache_format=packed"])
+    capsys.readouterr()
+    assert a["pitch_mean"] == b["pitch_mean"] and b["run"]["batches"] >= 2
+    cache = PackedCache(tmp_path / "pk" / "packed")
+    for k in range(5):
+        for t in ("log_mel", "pitch", "voiced_mask", "p_voiced", "energy"):
+            ref = torch.load(tmp_path / "pt" / t / f"u{k}.pt")
+            got = cache.load(t, f"u{k}")
+            assert got.dtype == ref.dtype and got.shape == ref.shape and torch.equal(got, ref), (t, k)
+    # resumed packed run: nothing left to do
+    c = X.main([f"manifest_filepath={mf}", f"sup_data_path={tmp_path / 'pk'}", types, "cache_format=packed"])
+    capsys.readouterr()
+    assert c is None or c.get("run", {}).get("utterances", 0) == 0

@@ -311,3 +311,33 @@ def test_native_pt_writer_matches_torch_save(tmp_path):
     assert torch.equal(torch.load(tmp_path / "ref.pt"), torch.load(paths[0]))
     with pytest.raises(Exception):
         H.pt_write_batch(base, np.array([0]), [(3,)], [str(tmp_path / "missing_dir" / "x.pt")], 1)
+
+
+def test_packed_cache_roundtrip_and_resample_plan(tmp_path):
+    """Row N1 packed format (writer + reader) and the resampler's host-side plan against scipy's output length."""
+    import torch
+    from scipy.signal import resample_poly
+    from roar_b200 import resample as R
+    from roar_b200.dataset_utils import PackedCache, write_packed_batch
+    base = torch.arange(1000, dtype=torch.float32)
+    idx = []
+    write_packed_batch(tmp_path, "r0_x_b000000", base, [0, 500, 900], [(1, 4, 10), (7,), (3,)],
+                       ["log_mel/a", "pitch/a", "pitch/b"], idx)
+    (tmp_path / "index_r0.jsonl").write_text("".join(idx))
+    c = PackedCache(tmp_path)
+    assert tuple(c.load("log_mel", "a").shape) == (1, 4, 10) and torch.equal(c.load("log_mel", "a").flatten(), base[:40])
+    assert torch.equal(c.load("pitch", "a"), base[500:507]) and torch.equal(c.load("pitch", "b"), base[900:903])
+    assert "pitch/b" in c and "energy/a" not in c and PackedCache.index_ids(tmp_path) == {"a", "b"}
+    x = np.random.default_rng(0).standard_normal(10007).astype(np.float32)
+    for a, b in ((44100, 22050), (48000, 22050), (16000, 22050), (22050, 16000)):
+        up, down, taps, n_pre_pad, n_pre_remove = R.plan(a, b)
+        y = resample_poly(x, up, down)
+        assert len(y) == int(R.out_len(len(x), up, down)) and taps.dtype == np.float32 and len(taps) == 20 * max(up, down) + 1
+        # the kernel's formula, evaluated here for a few outputs
+        for n in (0, 1, len(y) // 2, len(y) - 1):
+            c0 = (n + n_pre_remove) * down - n_pre_pad
+            k_hi = min(c0 // up, len(x) - 1) if c0 >= 0 else -1
+            k_lo = max(0, -(-(c0 - (len(taps) - 1)) // up))
+            ks = np.arange(k_lo, k_hi + 1)
+            assert abs(float((taps[c0 - ks * up].astype(np.float64) * x[ks]).sum()) - y[n]) <= 2e-6
+    assert R.plan(22050, 22050)[:2] == (1, 1)
