@@ -463,6 +463,16 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
             stats[0] = merge_partials(stats[0], part)
             stats[g] = merge_partials(stats[g], part)
 
+    packed = str(cfg.get("cache_format", "pt")).lower() == "packed"
+    packed_dir = (sup_path / "packed") if packed else None
+    packed_index: List[str] = []
+    run_id = f"{int(time.time()):x}"                           # shards of a resumed run never overwrite earlier ones
+    if packed:
+        packed_dir.mkdir(parents=True, exist_ok=True)
+        done = PackedCache.index_ids(packed_dir)              # utterances a previous packed run already holds
+        keep = [k for k, (uid, _) in enumerate(todo_ids) if uid not in done]
+        todo, todo_ids = [todo[k] for k in keep], [todo_ids[k] for k in keep]
+
     sr = scfg.sample_rate
     # batch composition from the manifest (duration, else file size): exact lengths come from the wav headers
     approx = np.array([int(items[i]["duration"] * sr) if items[i].get("duration") else
@@ -498,15 +508,6 @@ def run(cfg: dict) -> Optional[Dict[str, float]]:
 
     write_q: "queue.Queue" = queue.Queue()
     write_err: List[BaseException] = []
-    packed = str(cfg.get("cache_format", "pt")).lower() == "packed"
-    packed_dir = (sup_path / "packed") if packed else None
-    packed_index: List[str] = []
-    run_id = f"{int(time.time()):x}"                           # shards of a resumed run never overwrite earlier ones
-    if packed:
-        packed_dir.mkdir(parents=True, exist_ok=True)
-        done = PackedCache.index_ids(packed_dir)              # utterances a previous packed run already holds
-        keep = [k for k, (uid, _) in enumerate(todo_ids) if uid not in done]
-        todo, todo_ids = [todo[k] for k in keep], [todo_ids[k] for k in keep]
 
     def writer_loop():
         while True:
