@@ -222,6 +222,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
 //     reads one table component), the voiced row is filled with the sentinel, and the few candidate
 //     bins (4 per frame on average) are evaluated one per warp, lanes striding the sources.  Frames
 //     with lp_u < lt0 + 16 take the dense step (both voicings for every bin).
+//   * DEAD SEGMENTS.  When the unvoiced live list overflowed the band is scanned -- but a whole warp may still
+//     have nothing live in reach: per 32-bin segment the maximum of the new unvoiced values is kept, and a warp
+//     whose three segments in reach (w-1, w, w+1) all lie below the threshold thr' of the step that created them
+//     sees only dead sources there.  It skips the unvoiced band scan (sparse and dense steps, and the candidate
+//     evaluation of bins in such a segment): in voiced stretches only the bins within 25 per frame of the track
+//     are revived after a frame whose voiced probability clipped to 1 killed the unvoiced layer.
 // All rules only skip sources that lose strictly, so the decoded path is bit-identical to the dense
 // recursion (checked against it in tests/); values and back-pointers are identical for every state
 // that is not irrelevant in the sense above.
@@ -304,6 +310,8 @@ struct Vit3Step {
   const VitLive* Lu; int nu;
   double vmax; int kstar;      // first global arg-max of V[t-1]
   double vvmax;                // max over the voiced V[t-1] a destination of this warp can see in band
+  bool u_dead = false;         // every unvoiced source in reach of this warp's destinations is dead (below the
+                               //   liveness threshold of the step that created it): its band need not be scanned
   // tables
   const cf64* lt2;             // [n_rows+1][51] (ls, lc), last row zeros
   double lt0, lt_max;
@@ -321,10 +329,12 @@ HD void vit3_step_bin(const Vit3Step& c, int j, const uint32_t* rid, double lp_v
     if (dist > VIT_HW) { const double so = c.vmax + c.lt0; vit_offer(bv, so, c.kstar); vit_offer(bu, so, c.kstar); }
   }
   if (c.nu > VIT_LIST_MAX) {
-    double sb, wb; int sd, wd;
-    vit_band_scan(c.Vu + j, c.lt2, rid, &sb, &sd, &wb, &wd);
-    vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
-    vit_offer(bv, wb, c.npb + j - VIT_HW + wd);
+    if (!c.u_dead) {
+      double sb, wb; int sd, wd;
+      vit_band_scan(c.Vu + j, c.lt2, rid, &sb, &sd, &wb, &wd);
+      vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
+      vit_offer(bv, wb, c.npb + j - VIT_HW + wd);
+    }
   } else {
     for (int e = 0; e < c.nu; ++e) vit_list_offer(c.Lu[e], c.npb, c.lt2, j, bu, bv);
   }
@@ -388,10 +398,12 @@ HD VitBest2 vit4_unvoiced_scan(const Vit3Step& c, int j, const uint32_t* rid, co
   VitBest2 bu;
   bu.b = VIT_NEG; bu.a = 0x7fffffff;
   if (c.nu > VIT_LIST_MAX) {
-    double sb; int sd;
-    if (uniform_row) vit_band_scan1u(c.Vu + j, uniform_row, &sb, &sd);
-    else vit_band_scan1<0>(c.Vu + j, c.lt2, rid, &sb, &sd);
-    vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
+    if (!c.u_dead) {
+      double sb; int sd;
+      if (uniform_row) vit_band_scan1u(c.Vu + j, uniform_row, &sb, &sd);
+      else vit_band_scan1<0>(c.Vu + j, c.lt2, rid, &sb, &sd);
+      vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
+    }
   } else {
     for (int e = 0; e < c.nu; ++e) vit_list_offer1(c.Lu[e], c.npb, c.lt2, j, 0, bu);
   }
@@ -416,7 +428,7 @@ HD void vit4_unvoiced_finish(VitBest2 bu, int npb, double lt0, double vmax, int 
 
 // sparse step, candidate bin b (voiced destination): this lane's share of the offers.  `lane`/`nl`
 // stride the sources (nl = 1 on the host); the caller reduces the partials to (max, smallest index).
-HD VitBest2 vit4_cand_partial(const Vit3Step& c, const uint16_t* row_id, int b, int lane, int nl) {
+HD VitBest2 vit4_cand_partial(const Vit3Step& c, const uint16_t* row_id, int b, int lane, int nl, bool u_dead_b = false) {
   VitBest2 x;
   x.b = VIT_NEG; x.a = 0x7fffffff;
   if (lane == 0) {
@@ -425,10 +437,11 @@ HD VitBest2 vit4_cand_partial(const Vit3Step& c, const uint16_t* row_id, int b, 
     if (dist > VIT_HW) vit_offer(x, c.vmax + c.lt0, c.kstar);
   }
   if (c.nu > VIT_LIST_MAX) {
-    for (int d = lane; d < VIT_TW; d += nl) {
-      const int k = b - VIT_HW + d;
-      if (k >= 0 && k < c.npb) vit_offer(x, c.Vu[VIT_HW + k] + c.lt2[(int)row_id[k] * VIT_TW + (2 * VIT_HW - d)].y, c.npb + k);
-    }
+    if (!u_dead_b)
+      for (int d = lane; d < VIT_TW; d += nl) {
+        const int k = b - VIT_HW + d;
+        if (k >= 0 && k < c.npb) vit_offer(x, c.Vu[VIT_HW + k] + c.lt2[(int)row_id[k] * VIT_TW + (2 * VIT_HW - d)].y, c.npb + k);
+      }
   } else {
     for (int e = lane; e < c.nu; e += nl) vit_list_offer1(c.Lu[e], c.npb, c.lt2, b, 1, x);
   }
@@ -509,6 +522,7 @@ struct alignas(16) Vit3Shared {
   VitLive Lv[3][VIT_LIST_MAX];               // live lists: slot t % 3
   VitLive Lu[3][VIT_LIST_MAX];
   double wv[2][32], wvv[2][32];              // per-warp partials (= 32-bin segment stats)
+  double wuu[2][32];                         // maximum of the segment's unvoiced values (dead-segment rule)
   int wk[2][32];
   int cnt[3][2];
   int pub_kstar, pad_;
@@ -581,7 +595,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
   }
   vit_warp_argmax_neg(bestv, bestk);
   vvb = vit_warp_max(vvb);
-  if (lane == 0) { s.wv[0][warp] = bestv; s.wk[0][warp] = bestk; s.wvv[0][warp] = vvb; }
+  if (lane == 0) { s.wv[0][warp] = bestv; s.wk[0][warp] = bestk; s.wvv[0][warp] = vvb; s.wuu[0][warp] = 0.0; }   // 0.0: no bound yet
   __syncthreads();
 
   // One warp (`lead`, an interior one) reduces the block-wide quantities of a step -- first global
@@ -591,6 +605,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
   const int lead = nwarp >> 1;
   const int pfw = lead > 0 ? lead - 1 : 0;            // prefetch warp
   double prev_vmax = 0.0;                              // vmax is strictly decreasing in t
+  double thr_prev = VIT_NEG;                           // liveness threshold of the step that created the current sources
   uint16_t* pr = p.ptr + (size_t)(f0 + 1) * (2 * npb);
   for (int t = 1; t < T; ++t, pr += 2 * npb) {
     const int rp = (t - 1) & 1, wp = t & 1;           // V / partial parity: read, write
@@ -604,6 +619,16 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     if (tid < 2) s.cnt[zl][tid] = 0;
     const double lp_u = s.nxt_lpu[wp];
     nc_cur = s.nxt_nc[wp];
+    {   // dead-segment rule: the unvoiced values in reach of this warp's destinations against their creation threshold
+      double segu = s.wuu[rp][warp];
+      if (warp > 0) { const double x = s.wuu[rp][warp - 1]; segu = x > segu ? x : segu; }
+      if (warp + 1 < nwarp) { const double x = s.wuu[rp][warp + 1]; segu = x > segu ? x : segu; }
+      c.u_dead = segu < thr_prev;
+    }
+    VIT_STAT(13, (c.nu > VIT_LIST_MAX) ? 1 : 0);
+#ifdef ROAR_VIT_STATS
+    if (lane == 0 && c.nu > VIT_LIST_MAX) atomicAdd(&g_vit_stats[c.u_dead ? 14 : 15], 1ull);
+#endif
     double thr = 0.0;
     if (warp == lead) {
       double vmax = lane < nwarp ? s.wv[rp][lane] : VIT_NEG;
@@ -655,7 +680,15 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       // candidate bins of this frame: one per warp, lanes stride the sources
       for (int q = warp; q < nc_cur; q += nwarp) {
         const int b = s.cbin[wp][q];
-        VitBest2 x = vit4_cand_partial(c, s.rowid, b, lane, 32);
+        bool dead_b = false;
+        if (c.nu > VIT_LIST_MAX) {
+          const int sb = b >> 5;
+          double segu = s.wuu[rp][sb];
+          if (sb > 0) { const double y = s.wuu[rp][sb - 1]; segu = y > segu ? y : segu; }
+          if (sb + 1 < nwarp) { const double y = s.wuu[rp][sb + 1]; segu = y > segu ? y : segu; }
+          dead_b = segu < thr_prev;
+        }
+        VitBest2 x = vit4_cand_partial(c, s.rowid, b, lane, 32, dead_b);
         vit_warp_argmax_neg(x.b, x.a);
         if (lane == 0) {
           const double cv = s.clp[wp][q] + x.b;
@@ -715,7 +748,9 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     }
     vit_warp_argmax_neg(bestv, bestk);
     if (!sparse) vvb = vit_warp_max(vvb);     // sparse: 0.0 everywhere
-    if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; }
+    const double uub = vit_warp_max(j < npb ? nu : VIT_NEG);
+    if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; s.wuu[wp][warp] = uub; }
+    thr_prev = thr;
     __syncthreads();
   }
   if (warp == 0) {
