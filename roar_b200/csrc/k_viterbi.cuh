@@ -200,8 +200,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
 // are not visited:
 //   * DEAD sources.  Every destination j receives an offer >= fl(vmax + lt0) from the global arg-max
 //     k* (in band: fl(vmax + lt[k*,j]) with lt >= lt0; out of band: fl(vmax + lt0)).  A source s with
-//     V[s] < fl(vmax + lt0) offers fl(V[s] + lt) <= V[s] (lt < 0), strictly less: it never wins, never
-//     ties.  While step t computes V[t,.], each thread compares its two new values with
+//     fl(V[s] + lt_max) < fl(vmax + lt0) (lt_max = largest banded entry) offers fl(V[s] + lt) <=
+//     fl(V[s] + lt_max) in band (rounding is monotone), strictly less: it never wins, never ties (out of
+//     band only k* matters).  While step t computes V[t,.], each thread compares fl(new value + lt_max) with
 //     thr' = fl(LB + lt0), LB <= vmax_t being the value of the best one-step continuation of k*_{t-1}
 //     (known before the step), and appends the survivors to a per-voicing LIVE LIST.  thr' <= the true
 //     threshold, so the list is a superset of the live states.  Step t+1 walks the list when it holds
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       double segu = s.wuu[rp][warp];
       if (warp > 0) { const double x = s.wuu[rp][warp - 1]; segu = x > segu ? x : segu; }
       if (warp + 1 < nwarp) { const double x = s.wuu[rp][warp + 1]; segu = x > segu ? x : segu; }
-      c.u_dead = segu < thr_prev;
+      c.u_dead = segu + p.lt_max < thr_prev;
     }
     VIT_STAT(13, (c.nu > VIT_LIST_MAX) ? 1 : 0);
 #ifdef ROAR_VIT_STATS
@@ -686,7 +687,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
           double segu = s.wuu[rp][sb];
           if (sb > 0) { const double y = s.wuu[rp][sb - 1]; segu = y > segu ? y : segu; }
           if (sb + 1 < nwarp) { const double y = s.wuu[rp][sb + 1]; segu = y > segu ? y : segu; }
-          dead_b = segu < thr_prev;
+          dead_b = segu + p.lt_max < thr_prev;
         }
         VitBest2 x = vit4_cand_partial(c, s.rowid, b, lane, 32, dead_b);
         vit_warp_argmax_neg(x.b, x.a);
@@ -695,7 +696,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
           s.Vv[wp][VIT_HW + b] = cv;
           pr[b] = (uint16_t)x.a;
           if (cv > bestv || (cv == bestv && b < bestk)) { bestv = cv; bestk = b; }
-          if (cv >= thr) {
+          if (cv + p.lt_max >= thr) {
             const int pos = atomicAdd(&s.cnt[wl][0], 1);
             if (pos < VIT_LIST_MAX) { VitLive e; e.v = cv; e.kb = b; e.row = s.rowid[b]; s.Lv[wl][pos] = e; }
           }
@@ -708,7 +709,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
         s.Vu[wp][VIT_HW + j] = nu;
         pr[npb + j] = (uint16_t)au;
         if (nu > bestv || (nu == bestv && npb + j < bestk)) { bestv = nu; bestk = npb + j; }
-        live_u = nu >= thr;
+        live_u = nu + p.lt_max >= thr;
       }
       vvb = 0.0;     // no per-segment voiced maxima in a sparse step: an overflowing voiced list is scanned
     } else {
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
         pr[j] = (uint16_t)av; pr[npb + j] = (uint16_t)au;
         bestv = nv; bestk = j; vvb = nv;
         if (nu > bestv) { bestv = nu; bestk = npb + j; }
-        live_v = nv >= thr; live_u = nu >= thr;
+        live_v = nv + p.lt_max >= thr; live_u = nu + p.lt_max >= thr;
       }
     }
     prev_vmax = c.vmax;

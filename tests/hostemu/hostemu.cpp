@@ -208,7 +208,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     std::vector<uint32_t> rid((size_t)npb * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) vit_pack_rows(tb.row_id.data(), npb, tb.n_rows, j, rid.data() + (size_t)j * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) { Vv[VIT_HW + j] = V[j].x; Vu[VIT_HW + j] = V[j].y; }
-    long skipped = 0, listed = 0, n_sparse = 0, n_uniform = 0;
+    long skipped = 0, listed = 0, n_sparse = 0, n_uniform = 0, u_over = 0;
     bool sparse_prev = false;
     double prev_vmax = 0.0;
     for (int64_t t = 1; t < T; ++t) {
@@ -230,6 +230,8 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
       const double lb = vit3_lower_bound(c, tb.row_id.data(), lp_unv[t], cand_bin.data() + (size_t)t * g.kmax,
                                          cand_lp.data() + (size_t)t * g.kmax, n_cand[t], 0, 1);
       const double thr = lb + tb.lt0;
+      const double lmg = getenv("ROAR_EMU_WEAK") ? 0.0 : tb.lt_max;   // liveness margin (see k_viterbi.cuh)
+      if (c.nu > VIT_LIST_MAX) ++u_over;
       for (int q = 0; q < n_cand[t]; ++q) lpv[cand_bin[(size_t)t * g.kmax + q]] = cand_lp[(size_t)t * g.kmax + q];
       const bool sparse = lp_unv[t] >= tb.lt0 + VIT_SPARSE_MARGIN;
       if (sparse) {
@@ -245,7 +247,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
           const double cv = cand_lp[(size_t)t * g.kmax + q] + x.b;
           Vv[(size_t)wp * VP + VIT_HW + b] = cv;
           ptr[(size_t)t * 2 * npb + b] = (uint16_t)x.a;
-          if (cv >= thr) { if (cnt[wl][0] < VIT_LIST_MAX) { VitLive e; e.v = cv; e.kb = b; e.row = tb.row_id[b]; Lv[(size_t)wl * VIT_LIST_MAX + cnt[wl][0]] = e; } ++cnt[wl][0]; }
+          if (cv + lmg >= thr) { if (cnt[wl][0] < VIT_LIST_MAX) { VitLive e; e.v = cv; e.kb = b; e.row = tb.row_id[b]; Lv[(size_t)wl * VIT_LIST_MAX + cnt[wl][0]] = e; } ++cnt[wl][0]; }
         }
         c.vvmax = 0.0;   // placeholder, replaced per bin below
       }
@@ -275,9 +277,9 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
           vit3_step_bin(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lpv[j], lp_unv[t], &nv, &nu, &av, &au);
           Vv[(size_t)wp * VP + VIT_HW + j] = nv; Vu[(size_t)wp * VP + VIT_HW + j] = nu;
           ptr[(size_t)t * 2 * npb + j] = (uint16_t)av; ptr[(size_t)t * 2 * npb + npb + j] = (uint16_t)au;
-          if (nv >= thr) { if (cnt[wl][0] < VIT_LIST_MAX) { VitLive e; e.v = nv; e.kb = j; e.row = tb.row_id[j]; Lv[(size_t)wl * VIT_LIST_MAX + cnt[wl][0]] = e; } ++cnt[wl][0]; }
+          if (nv + lmg >= thr) { if (cnt[wl][0] < VIT_LIST_MAX) { VitLive e; e.v = nv; e.kb = j; e.row = tb.row_id[j]; Lv[(size_t)wl * VIT_LIST_MAX + cnt[wl][0]] = e; } ++cnt[wl][0]; }
         }
-        if (nu >= thr) { if (cnt[wl][1] < VIT_LIST_MAX) { VitLive e; e.v = nu; e.kb = j; e.row = tb.row_id[j]; Lu[(size_t)wl * VIT_LIST_MAX + cnt[wl][1]] = e; } ++cnt[wl][1]; }
+        if (nu + lmg >= thr) { if (cnt[wl][1] < VIT_LIST_MAX) { VitLive e; e.v = nu; e.kb = j; e.row = tb.row_id[j]; Lu[(size_t)wl * VIT_LIST_MAX + cnt[wl][1]] = e; } ++cnt[wl][1]; }
       }
       sparse_prev = sparse;
       prev_vmax = c.vmax;
@@ -285,7 +287,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     }
     const int lp_ = (int)((T - 1) & 1);
     for (int j = 0; j < npb; ++j) { V[(size_t)lp_ * npb + j].x = Vv[(size_t)lp_ * VP + VIT_HW + j]; V[(size_t)lp_ * npb + j].y = Vu[(size_t)lp_ * VP + VIT_HW + j]; }
-    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps, %ld sparse steps, %ld uniform bin-steps (uniform_vmax %g)\n", listed, skipped, n_sparse, n_uniform, tb.uniform_vmax);
+    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps, %ld sparse steps, %ld uniform bin-steps (uniform_vmax %g), %ld unvoiced-overflow steps of %ld\n", listed, skipped, n_sparse, n_uniform, tb.uniform_vmax, u_over, (long)T - 1);
   } else {
   for (int64_t t = 1; t < T; ++t) {
     const cf64* Vc = V.data() + (size_t)((t - 1) & 1) * npb;
