@@ -630,8 +630,29 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
       if (lane == 0) s.cnt[32] = base;
     }
     __syncwarp();
-    prob_phase3(p, s, lane, thr); __syncwarp();
-    prob_phase4(p, s, lane); __syncwarp();
+    {   // prob_phase3 + prob_phase4: first threshold per trough; global minimum trough (lowest height, first index)
+        // by a shuffle arg-min over the per-lane partials instead of a serial pass of lane 0
+      const int R = s.cnt[32];
+      double best = 1e300; int bi = 0x7fffffff;
+      for (int r = lane; r < R; r += 32) {
+        const double h = s.x[s.tr[r]];
+        int lo = 0, hi = p.n_thr;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (thr[mid] <= h) lo = mid; else hi = mid - 1;
+        }
+        s.cr[r] = (uint8_t)lo;
+        if (h < best) { best = h; bi = r; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double oh = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oh < best || (oh == best && oi < bi)) { best = oh; bi = oi; }
+      }
+      if (lane == 0) s.cnt[33] = bi;
+    }
+    __syncwarp();
     {
       const int R = s.cnt[32];
       // compact the active troughs in lag order
@@ -669,43 +690,92 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
         const bool more = base + 32 < na;
         double acc = 0.0, K = 0.0;     // K = fact[n_c] * exp(-lambda * pos): changes only where a trough starts
         int pos = 0, n = 0;
-        for (int c = cmin; c < p.n_thr; ++c) {
-          const int hc = hist[c];      // warp-uniform
-          if (hc) {
-            const unsigned m = __ballot_sync(0xffffffffu, cr == c);
-            const int cy = carry[c];
-            n += hc;
-            pos += cy + __popc(m & lt_mask);
-            if (more && lane == 0 && m) carry[c] = cy + __popc(m);
-            K = bfact[n] * bexp[pos];
+        if (p.n_thr <= 128) {
+          // thresholds where some active trough starts (hist != 0) as a bit mask; between two of them K is
+          // constant, so the inner loop is just  acc += K * beta[c]  (same additions, same order)
+          unsigned nzm[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) nzm[w] = __ballot_sync(0xffffffffu, 32 * w + lane < p.n_thr && hist[32 * w + lane] != 0);
+          int c = cmin;
+          while (c < p.n_thr) {
+            {   // change point c
+              const unsigned m = __ballot_sync(0xffffffffu, cr == c);
+              const int cy = carry[c];
+              n += hist[c];
+              pos += cy + __popc(m & lt_mask);
+              if (more && lane == 0 && m) carry[c] = cy + __popc(m);
+              K = bfact[n] * bexp[pos];
+            }
+            int cn = p.n_thr;       // next change point
+#pragma unroll
+            for (int w = 3; w >= 0; --w) {
+              unsigned mw = nzm[w];
+              if (c >= 32 * w) mw = c >= 32 * w + 31 ? 0u : mw & (0xfffffffeu << (c - 32 * w));
+              if (mw) cn = 32 * w + __ffs(mw) - 1;
+            }
+            int cc = c > cr ? c : cr;
+            for (; cc < cn; ++cc) acc += K * beta[cc];
+            c = cn;
           }
-          if (c >= cr) acc += K * beta[c];
+        } else {
+          for (int c = cmin; c < p.n_thr; ++c) {
+            const int hc = hist[c];      // warp-uniform
+            if (hc) {
+              const unsigned m = __ballot_sync(0xffffffffu, cr == c);
+              const int cy = carry[c];
+              n += hc;
+              pos += cy + __popc(m & lt_mask);
+              if (more && lane == 0 && m) carry[c] = cy + __popc(m);
+              K = bfact[n] * bexp[pos];
+            }
+            if (c >= cr) acc += K * beta[c];
+          }
         }
         if (r >= 0) prob_trough_finish(p, s, r, acc);
         __syncwarp();
       }
     }
     __syncwarp();
-    prob_phase6a(p, s, lane); __syncwarp();
+    {   // prob_phase6a: a trough survives NumPy's last-write-wins scatter unless the NEXT trough with a non-zero
+        // probability lands on the same pitch bin.  Bins are non-increasing in lag order (troughs are at least two
+        // lags apart and the parabolic shift is < 1 in magnitude, so refined periods strictly increase), hence
+        // duplicates of a bin are adjacent among the non-zero troughs: one look at the successor decides.
+        // Chunks of 32 troughs from the last to the first, the successor's bin carried across chunks.
+      const int R = s.cnt[32];
+      int nb = -2;                                   // bin of the nearest non-zero trough after this chunk
+      for (int base = ((R - 1) >> 5) << 5; base >= 0; base -= 32) {
+        const int r = base + lane;
+        const int b = r < R ? (int)s.bin[r] : -1;
+        const unsigned nz = __ballot_sync(0xffffffffu, b >= 0);
+        const unsigned above = lane == 31 ? 0u : nz >> (lane + 1);
+        const int src = above ? lane + __ffs(above) : lane;
+        const int sb = __shfl_sync(0xffffffffu, b, src);
+        const int nxt = above ? sb : nb;
+        if (r < R) s.live[r] = (b >= 0 && b < p.npb && nxt != b) ? 1 : 0;
+        if (nz) nb = __shfl_sync(0xffffffffu, b, __ffs(nz) - 1);
+      }
+    }
+    __syncwarp();
     {   // prob_phase6b with the logarithms spread over the lanes; the voiced-probability sum stays serial
       const int R = s.cnt[32];
       uint16_t* ob = p.cand_bin + (size_t)frame * p.kmax;
       double* ol = p.cand_lp + (size_t)frame * p.kmax;
       int n = 0;
+      double vp = 0.0;     // summed in descending trough order (= ascending pitch bin), every lane the same chain
       for (int b0 = 0; b0 < R; b0 += 32) {
         const int r = R - 1 - (b0 + lane);
         const bool live = r >= 0 && s.live[r];
         const unsigned m = __ballot_sync(0xffffffffu, live);
+        const double pr = live ? s.prob[r] : 0.0;
         if (live) {
           const int pos = n + __popc(m & ((1u << lane) - 1u));
           ob[pos] = (uint16_t)s.bin[r];
-          ol[pos] = log(s.prob[r] + 2.2250738585072014e-308);
+          ol[pos] = log(pr + 2.2250738585072014e-308);
         }
+        for (unsigned mm = m; mm; mm &= mm - 1) vp += __shfl_sync(0xffffffffu, pr, __ffs(mm) - 1);
         n += __popc(m);
       }
       if (lane == 0) {
-        double vp = 0.0;
-        for (int r = R - 1; r >= 0; --r) if (s.live[r]) vp += s.prob[r];
         if (vp < 0.0) vp = 0.0;
         if (vp > 1.0) vp = 1.0;
         p.n_cand[frame] = n;
