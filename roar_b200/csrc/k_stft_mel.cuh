@@ -50,6 +50,8 @@ struct StftParams {
   const int32_t* mel_offset;
   const float* mel_w;         // packed band weights
   int32_t mel_nw;
+  int32_t tw_total;           // fft_tw_total(M), computed once on the host (0: derive it)
+  int32_t part_per_slot;      // energy partials per frame slot in StftSmem::part (0: one per thread = P)
 };
 
 // shared-memory carve-up (all offsets in bytes, 16-B aligned)
@@ -75,7 +77,7 @@ HD size_t stft_smem_carve(const StftParams& p, int nthreads, unsigned char* base
   CARVE(mbar, unsigned long long, 2)
   CARVE(audio, float, p.span)
   CARVE(window, float, p.n_fft)
-  CARVE(tw, cf32, fft_tw_total(p.M) + 1)
+  CARVE(tw, cf32, (p.tw_total ? p.tw_total : fft_tw_total(p.M)) + 1)
   CARVE(bufA, cf32, (size_t)p.G * pidx(p.M) + 8)
   CARVE(bufB, cf32, (size_t)p.G * pidx(p.M) + 8)
   CARVE(part, float, nthreads)
@@ -148,7 +150,7 @@ HD float stft_sample(const StftParams& p, const StftTile& t, int64_t pos) {
 HD void stft_phase_tables(const StftParams& p, StftSmem& s, int tid, int nthr) {
   for (int i = tid; i < p.n_fft; i += nthr) s.window[i] = p.window[i];
   {
-    const int nt = fft_tw_total(p.M);
+    const int nt = p.tw_total ? p.tw_total : fft_tw_total(p.M);
     for (int i = tid; i < nt; i += nthr) s.tw[i] = p.tw[i];
   }
   for (int i = tid; i < p.n_mels; i += nthr) {
@@ -220,55 +222,87 @@ HD float stft_pow(float mag, float power) {
   return powf(mag, power);
 }
 
-// ---- untangle the real FFT, magnitude (+ floor), power, energy partials
-HD void stft_phase_post(const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid,
-                        const cf32* z_base, float* spec_base) {
+// ---- untangle the real FFT, magnitude (+ floor), power, energy partials.
+// Bins k and M-k come from the same pair (Z[k], Z[M-k]):  X[k] = e + t,  X[M-k] = conj(e - t)  with
+// e = (Z[k] + conj Z[M-k]) / 2,  t = W_N^k (Z[k] - conj Z[M-k]) / (2i)   (W_N^{M-k} = -conj W_N^k),
+// so one thread does both: half the shared-memory reads and one complex product per two bins.
+// Returns the thread's share of sum |X|^2 (also parked in s.part[tid] when there is one partial per thread).
+HD float stft_phase_post(const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid,
+                         const cf32* z_base, float* spec_base) {
   const int slot = tid / p.P, u = tid - slot * p.P;
   const int f = g * p.G + slot;
   float esum = 0.f;
   if (f < t.nf) {
     const cf32* Z = z_base + (size_t)slot * pidx(p.M);
     float* spec = spec_base + (size_t)slot * (2 * pidx(p.M));
-    for (int k = u; k <= p.M; k += p.P) {
-      const cf32 zk = Z[pidx(k & (p.M - 1))];
+    const int half = p.M >> 1;
+    for (int k = u; k <= half; k += p.P) {
+      const cf32 zk = Z[pidx(k)];
       const cf32 zc = cconj(Z[pidx((p.M - k) & (p.M - 1))]);
-      // X[k] = (zk+zc)/2 + W_N^k * (zk-zc)/(2i)
       cf32 e; e.x = 0.5f * (zk.x + zc.x); e.y = 0.5f * (zk.y + zc.y);
       cf32 d; d.x = 0.5f * (zk.y - zc.y); d.y = -0.5f * (zk.x - zc.x);   // (zk-zc)/(2i)
       const cf32 w = ld_ro(p.tw_post + k);
-      const float re = e.x + (w.x * d.x - w.y * d.y);
-      const float im = e.y + (w.x * d.y + w.y * d.x);
+      const float tx = w.x * d.x - w.y * d.y, ty = w.x * d.y + w.y * d.x;
+      const float re = e.x + tx, im = e.y + ty;
       const float mag = stft_sqrt(re * re + im * im + p.floor_);
       esum += mag * mag;
       spec[k] = stft_pow(mag, p.mag_power);
+      if (k != p.M - k) {
+        const float re2 = e.x - tx, im2 = e.y - ty;
+        const float mag2 = stft_sqrt(re2 * re2 + im2 * im2 + p.floor_);
+        esum += mag2 * mag2;
+        spec[p.M - k] = stft_pow(mag2, p.mag_power);
+      }
     }
   }
-  s.part[tid] = esum;
+  if (p.part_per_slot == 0) s.part[tid] = esum;
+  return esum;
 }
 
-// ---- sparse mel rows + log guard (+ the energy reduction as extra work items)
+// ---- sparse mel rows + log guard (+ the energy reduction as extra work items).
+// One work item = one mel band for a PAIR of frame slots: the band's weights are read once for both frames,
+// and G/2 * n_mels items fit the CTA in one round (the per-slot mapping needed two, the second a quarter full).
+HD float stft_mel_log(const StftParams& p, float acc) {
+  if (p.log_mode == ROAR_LOG_CLAMP) return logf(acc < p.log_guard ? p.log_guard : acc);
+  if (p.log_mode == ROAR_LOG_ADD) return logf(acc + p.log_guard);
+  return acc;
+}
 HD void stft_phase_mel(const StftParams& p, const StftTile& t, StftSmem& s, int g, int tid, int nthr,
                        const float* spec_base) {
-  const int per = p.n_mels + 1;
-  for (int w = tid; w < p.G * per; w += nthr) {
-    const int slot = w / per, m = w - slot * per;
-    const int f = g * p.G + slot;
-    if (f >= t.nf) continue;
-    if (m == p.n_mels) {
+  const int pairs = (p.G + 1) >> 1;
+  const int n_items = pairs * p.n_mels;
+  const int pps = p.part_per_slot ? p.part_per_slot : p.P;
+  const size_t sstride = (size_t)(2 * pidx(p.M));
+  for (int w = tid; w < n_items + p.G; w += nthr) {
+    if (w >= n_items) {                      // energy of one frame slot
+      const int slot = w - n_items;
+      const int f = g * p.G + slot;
+      if (f >= t.nf) continue;
       float e = 0.f;
-      const float* pp = s.part + slot * p.P;
-      for (int i = 0; i < p.P; ++i) e += pp[i];
+      const float* pp = s.part + slot * pps;
+      for (int i = 0; i < pps; ++i) e += pp[i];
       s.en[f] = sqrtf(e);
       continue;
     }
-    const float* spec = spec_base + (size_t)slot * (2 * pidx(p.M)) + s.mel_start[m];
+    const int sp = w / p.n_mels, m = w - sp * p.n_mels;
+    const int slot0 = 2 * sp, slot1 = slot0 + 1;
+    const int f0 = g * p.G + slot0, f1 = f0 + 1;
+    if (f0 >= t.nf) continue;
+    const bool two = slot1 < p.G && f1 < t.nf;
+    const float* sa = spec_base + (size_t)slot0 * sstride + s.mel_start[m];
+    const float* sb = two ? sa + sstride : sa;
     const float* wgt = s.mel_w + s.mel_offset[m];
     const int cnt = s.mel_count[m];
-    float acc = 0.f;
-    for (int c = 0; c < cnt; ++c) acc += wgt[c] * spec[c];
-    if (p.log_mode == ROAR_LOG_CLAMP) acc = logf(acc < p.log_guard ? p.log_guard : acc);
-    else if (p.log_mode == ROAR_LOG_ADD) acc = logf(acc + p.log_guard);
-    s.out[m * (p.FT + 1) + f] = acc;
+    float a0 = 0.f, a1 = 0.f;
+    int c = 0;
+    for (; c + 1 < cnt; c += 2) {
+      const float w0 = wgt[c], w1 = wgt[c + 1];
+      a0 += w0 * sa[c]; a1 += w0 * sb[c];
+      a0 += w1 * sa[c + 1]; a1 += w1 * sb[c + 1];
+    }
+    if (c < cnt) { const float w0 = wgt[c]; a0 += w0 * sa[c]; a1 += w0 * sb[c]; }
+    s.out[m * (p.FT + 1) + f0] = stft_mel_log(p, a0);
+    if (two) s.out[m * (p.FT + 1) + f1] = stft_mel_log(p, a1);
   }
 }
 
@@ -387,7 +421,14 @@ __global__ void __launch_bounds__(256) k_stft_mel(const StftParams p) {
     }
     const cf32* zfin = src;            // FFT result
     float* spec = (float*)dst;         // the other buffer holds |X| for the mel phase
-    stft_phase_post(p, t, s, g, tid, zfin, spec);
+    {
+      float esum = stft_phase_post(p, t, s, g, tid, zfin, spec);
+      if (p.part_per_slot) {          // P >= 32: a warp lies inside one frame slot -> one partial per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+        if ((tid & 31) == 0) s.part[tid >> 5] = esum;
+      }
+    }
     __syncthreads();
     stft_phase_mel(p, t, s, g, tid, nthr, spec);
     __syncthreads();

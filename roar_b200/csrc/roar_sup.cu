@@ -115,6 +115,8 @@ static StftParams stft_params_base(const roar_sup_handle* h) {
   p.window = h->d_window; p.tw = h->d_tw; p.tw_post = h->d_tw_post;
   p.mel_start = h->d_mel_start; p.mel_count = h->d_mel_count; p.mel_offset = h->d_mel_offset;
   p.mel_w = h->d_mel_w; p.mel_nw = h->mel_nw;
+  p.tw_total = fft_tw_total(g.M);
+  p.part_per_slot = h->stft_P >= 32 && h->stft_P % 32 == 0 ? h->stft_P / 32 : 0;
   return p;
 }
 
