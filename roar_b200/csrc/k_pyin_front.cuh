@@ -128,17 +128,21 @@ HD void cmnd_phase_load(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
   // energy terms first: asynchronous 4-byte copies on the device, consumed after the autocorrelation
   // (consecutive threads take consecutive frames of one lag: the global reads stay sector-coalesced)
   const float* Eg = p.energy + (p.frame_off[t.utt] + t.t0);
-  const int ne = (p.max_period + 1) * t.nf;
-  for (int i = tid; i < ne; i += nthr) {
-    const int tau = i / t.nf, f = i - tau * t.nf;
-    const float* src = Eg + (size_t)tau * p.total_frames + f;
-    float* dst = s.E + tau * p.FT + f;
+  {   // LW lanes per lag (LW >= FT, a power of two): frame = tid & (LW-1), no division per element
+    const int lw_log = p.FT <= 16 ? 4 : 5, LW = 1 << lw_log;
+    const int f = tid & (LW - 1);
+    if (f < t.nf) {
+      for (int tau = tid >> lw_log; tau <= p.max_period; tau += nthr >> lw_log) {
+        const float* src = Eg + (size_t)tau * p.total_frames + f;
+        float* dst = s.E + tau * p.FT + f;
 #if defined(__CUDA_ARCH__)
-    const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d32), "l"(src) : "memory");
+        const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d32), "l"(src) : "memory");
 #else
-    *dst = *src;
+        *dst = *src;
 #endif
+      }
+    }
   }
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -353,9 +357,11 @@ HD void cmnd_phase_emit(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
   const double* d = s.Q + (size_t)f * cmnd_qs(p);
   const double* ds = s.dsum + (size_t)slot * (p.max_period + 1);
   double* out = p.cmnd + (size_t)(p.frame_off[t.utt] + t.t0 + f) * p.n_lags;
+  // (tau - 1) / ch by a multiply-shift: exact for tau - 1 < 2^20 / ch (tau <= max_period ~ 1.4 k, ch >= 1)
+  const unsigned chm = ((1u << 20) + (unsigned)ch - 1u) / (unsigned)ch;
   for (int i = u; i < p.n_lags; i += 32) {
     const int tau = p.min_period + i;
-    const double c = ds[tau] + s.chunk[slot * 64 + 32 + (tau - 1) / ch];
+    const double c = ds[tau] + s.chunk[slot * 64 + 32 + (int)(((unsigned)(tau - 1) * chm) >> 20)];
     out[i] = d[tau] / (c / (double)tau + 2.2250738585072014e-308);
   }
 }
