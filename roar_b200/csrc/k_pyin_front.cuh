@@ -47,6 +47,7 @@ struct PyinParams {
   // scratch / outputs
   float* energy;              // [max_period+1, total_frames]  E[tau] = cs[W+tau] - cs[tau] (float32 scratch, frame-contiguous)
   const int32_t* etile_off;   // [n_utts+1] prefix sum of ceil(T_i / 32): energy-kernel tiles
+  const int32_t* etile_map;   // [n_etiles] energy tile -> utterance (optional: null = binary search of etile_off)
   double* cmnd;               // [total_frames, n_lags]
   uint16_t* cand_bin;         // [total_frames, kmax]
   double* cand_lp;            // [total_frames, kmax]
@@ -221,6 +222,35 @@ HD int energy_span(const PyinParams& p) { return (ENERGY_FT - 1) * p.hop + p.W +
 HD void pyin_energy_stage(const PyinParams& p, const float* y, int L, int64_t q0, int n, float* sq, int tid,
                           int nthr) {
   const int hop = p.hop;
+#if defined(__CUDA_ARCH__)
+  // groups of 4 samples: one 16-byte load when the group lies inside the utterance, inside one hop-sized
+  // segment of the padded layout and the source is aligned; scalar loads at the edges
+  if ((hop & 3) == 0) {
+    const bool aligned = (((reinterpret_cast<uintptr_t>(y) >> 2) + (uintptr_t)(q0 & 3)) & 3) == 0;
+    const int n4 = (n + 3) >> 2;
+    for (int g = tid; g < n4; g += nthr) {
+      const int i0 = g << 2;                       // sample index in the tile; hop % 4 == 0: one segment
+      const int sg = i0 / hop;
+      float* dst = sq + (size_t)sg * (hop + 1) + (i0 - sg * hop);
+      const int64_t q = q0 + i0;
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+      if (aligned && q >= 0 && q + 3 < L) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(y + q));
+        v0 = x.x; v1 = x.y; v2 = x.z; v3 = x.w;
+      } else {
+        if (q >= 0 && q < L) v0 = y[q];
+        if (q + 1 >= 0 && q + 1 < L) v1 = y[q + 1];
+        if (q + 2 >= 0 && q + 2 < L) v2 = y[q + 2];
+        if (q + 3 >= 0 && q + 3 < L) v3 = y[q + 3];
+      }
+      dst[0] = f32_mul(v0, v0);
+      if (i0 + 1 < n) dst[1] = f32_mul(v1, v1);
+      if (i0 + 2 < n) dst[2] = f32_mul(v2, v2);
+      if (i0 + 3 < n) dst[3] = f32_mul(v3, v3);
+    }
+    return;
+  }
+#endif
   for (int s0 = 0, sg = 0; s0 < n; s0 += hop, ++sg) {
     const int len = n - s0 < hop ? n - s0 : hop;
     float* dst = sq + (size_t)sg * (hop + 1);
@@ -558,9 +588,13 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_pyin_energy(const PyinParams
   const int tile = blockIdx.x, tid = threadIdx.x;
   if (tile >= p.etile_off[p.n_utts]) return;
   int lo = 0, hi = p.n_utts;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (p.etile_off[mid] <= tile) lo = mid; else hi = mid;
+  if (p.etile_map) {
+    lo = p.etile_map[tile];
+  } else {
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.etile_off[mid] <= tile) lo = mid; else hi = mid;
+    }
   }
   const int T = (int)(p.frame_off[lo + 1] - p.frame_off[lo]);
   const int t0 = (tile - p.etile_off[lo]) * ENERGY_FT;

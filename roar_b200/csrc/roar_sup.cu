@@ -546,12 +546,17 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
   p.audio = d_audio; p.sample_off = d_sample_off; p.sample_len = d_sample_len; p.frame_off = d_frame_off;
   p.tile_off = w.tile_off; p.n_utts = n_utts; p.cmnd = w.big; p.energy = w.energy; p.etile_off = w.etile_off; p.cand_bin = w.cand_bin; p.cand_lp = w.cand_lp;
   p.n_cand = w.n_cand; p.lp_unvoiced = w.lp_unv; p.voiced_prob = d_vprob; p.total_frames = total_frames;
+  // the tile -> utterance map region serves the energy kernel first (its tiles are the fewer), then K2a
+  const int64_t max_etiles = total_frames / ENERGY_FT + n_utts;
+  LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, ENERGY_FT, w.etile_off));
+  k_tile_map<<<(unsigned)((max_etiles + 255) / 256), 256, 0, st>>>(w.etile_off, n_utts, w.tile_map);
+  p.etile_map = w.tile_map;
+  LAUNCH(h, ROAR_K_PYIN_ENERGY, st, k_pyin_energy<<<(unsigned)max_etiles, ENERGY_THREADS, h->energy_smem, st>>>(p));
+  p.etile_map = nullptr;
   LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, p.FT, w.tile_off));
   const int64_t max_tiles = total_frames / p.FT + n_utts;
   k_tile_map<<<(unsigned)((max_tiles + 255) / 256), 256, 0, st>>>(w.tile_off, n_utts, w.tile_map);
   p.tile_map = w.tile_map;
-  LAUNCH(h, ROAR_K_TILE_OFFSETS, st, k_tile_offsets<<<1, 1024, 0, st>>>(d_frame_off, n_utts, ENERGY_FT, w.etile_off));
-  LAUNCH(h, ROAR_K_PYIN_ENERGY, st, k_pyin_energy<<<(unsigned)(total_frames / ENERGY_FT + n_utts), ENERGY_THREADS, h->energy_smem, st>>>(p));
   LAUNCH(h, ROAR_K_PYIN_CMND, st, k_pyin_cmnd<<<(unsigned)max_tiles, CMND_THREADS, h->cmnd_smem, st>>>(p));
   int64_t pb = (total_frames + 7) / 8;
   const int64_t cap = (int64_t)h->sm_count * 16;
