@@ -526,7 +526,7 @@ struct alignas(16) Vit3Shared {
   double wuu[2][32];                         // maximum of the segment's unvoiced values (dead-segment rule)
   int wk[2][32];
   int cnt[3][2];
-  int pub_kstar, pad_;
+  int pub_kstar, pub_doa;                    // pub_doa: dead-on-arrival dense step (see the kernel)
   double pub_vmax, pub_thr;                  // block-wide values of the running step (written by the lead warp)
   double nxt_lpu[2];                         // unvoiced observation / candidate count of frame f at [f & 1]
   int nxt_nc[2];                             //   (written one step ahead by the prefetch warp)
@@ -548,6 +548,33 @@ __device__ __forceinline__ void vit3_append(bool live, double v, int kb, int row
     if (pos < VIT_LIST_MAX) { VitLive e; e.v = v; e.kb = kb; e.row = row; L[pos] = e; }
   }
 }
+
+// candidate bins of the frame being entered: one per warp, lanes stride the sources (sparse steps and
+// dead-on-arrival dense steps)
+#define VIT_CAND_LOOP \
+      for (int q = warp; q < nc_cur; q += nwarp) { \
+        const int b = s.cbin[wp][q]; \
+        bool dead_b = false; \
+        if (c.nu > VIT_LIST_MAX) { \
+          const int sb = b >> 5; \
+          double segu = s.wuu[rp][sb]; \
+          if (sb > 0) { const double y = s.wuu[rp][sb - 1]; segu = y > segu ? y : segu; } \
+          if (sb + 1 < nwarp) { const double y = s.wuu[rp][sb + 1]; segu = y > segu ? y : segu; } \
+          dead_b = segu + p.lt_max < thr_prev; \
+        } \
+        VitBest2 x = vit4_cand_partial(c, s.rowid, b, lane, 32, dead_b); \
+        vit_warp_argmax_neg(x.b, x.a); \
+        if (lane == 0) { \
+          const double cv = s.clp[wp][q] + x.b; \
+          s.Vv[wp][VIT_HW + b] = cv; \
+          pr[b] = (uint16_t)x.a; \
+          if (cv > bestv || (cv == bestv && b < bestk)) { bestv = cv; bestk = b; } \
+          if (cv + p.lt_max >= thr) { \
+            const int pos = atomicAdd(&s.cnt[wl][0], 1); \
+            if (pos < VIT_LIST_MAX) { VitLive e; e.v = cv; e.kb = b; e.row = s.rowid[b]; s.Lv[wl][pos] = e; } \
+          } \
+        } \
+      }
 
 // blockDim.x = npb rounded up to a warp multiple (<= 608); two CTAs (utterances) per SM
 __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
@@ -640,7 +667,14 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       double lb = vit3_lower_bound(c, s.rowid, lp_u, s.cbin[wp], s.clp[wp], nc_cur, lane, 32);
       lb = vit_warp_max(lb);
       thr = lb + p.lt0;
-      if (lane == 0) { s.pub_vmax = vmax; s.pub_thr = thr; s.pub_kstar = kstar; }
+      // DEAD ON ARRIVAL.  No offer exceeds fl(vmax + lt_max), so a destination with observation lp ends at or
+      // below U(lp) = fl(lp + fl(vmax + lt_max)); if fl(U + lt_max) < thr it is dead the moment it is created
+      // (liveness test of the next step), i.e. neither its value nor its back-pointer can ever be read.  When
+      // that holds for lp = lt0 (voiced states without a candidate) and for lp = lp_u (all unvoiced states) --
+      // the frames whose voiced probability clipped to 1 -- a dense step only evaluates the candidate bins.
+      const double top = vmax + p.lt_max;
+      const int doa = (((p.lt0 + top) + p.lt_max) < thr && ((lp_u + top) + p.lt_max) < thr) ? 1 : 0;
+      if (lane == 0) { s.pub_vmax = vmax; s.pub_thr = thr; s.pub_kstar = kstar; s.pub_doa = doa; }
       asm volatile("bar.arrive 1, %0;" ::"r"(nthr) : "memory");
     }
     // one warp prefetches the next frame's sparse observations for the block (loads issued here, stored
@@ -657,6 +691,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     bool live_v = false, live_u = false;
     double nv = VIT_NEG, nu = VIT_NEG;
     const bool sparse = lp_u >= p.lt0 + VIT_SPARSE_MARGIN;     // block-uniform
+    bool doa_step = false;
     VIT_STAT(sparse ? 0 : 1, 1);
     VIT_STAT(c.nu > VIT_LIST_MAX ? 2 : 4, 1);
     VIT_STAT(c.nv > VIT_LIST_MAX ? 3 : 5, 1);
@@ -678,30 +713,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
         asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
         c.vmax = s.pub_vmax; c.kstar = s.pub_kstar; thr = s.pub_thr;
       }
-      // candidate bins of this frame: one per warp, lanes stride the sources
-      for (int q = warp; q < nc_cur; q += nwarp) {
-        const int b = s.cbin[wp][q];
-        bool dead_b = false;
-        if (c.nu > VIT_LIST_MAX) {
-          const int sb = b >> 5;
-          double segu = s.wuu[rp][sb];
-          if (sb > 0) { const double y = s.wuu[rp][sb - 1]; segu = y > segu ? y : segu; }
-          if (sb + 1 < nwarp) { const double y = s.wuu[rp][sb + 1]; segu = y > segu ? y : segu; }
-          dead_b = segu + p.lt_max < thr_prev;
-        }
-        VitBest2 x = vit4_cand_partial(c, s.rowid, b, lane, 32, dead_b);
-        vit_warp_argmax_neg(x.b, x.a);
-        if (lane == 0) {
-          const double cv = s.clp[wp][q] + x.b;
-          s.Vv[wp][VIT_HW + b] = cv;
-          pr[b] = (uint16_t)x.a;
-          if (cv > bestv || (cv == bestv && b < bestk)) { bestv = cv; bestk = b; }
-          if (cv + p.lt_max >= thr) {
-            const int pos = atomicAdd(&s.cnt[wl][0], 1);
-            if (pos < VIT_LIST_MAX) { VitLive e; e.v = cv; e.kb = b; e.row = s.rowid[b]; s.Lv[wl][pos] = e; }
-          }
-        }
-      }
+      VIT_CAND_LOOP
       if (j < npb) {
         int au;
         vit4_unvoiced_finish(bu, npb, p.lt0, c.vmax, c.kstar, j, lp_u, &nu, &au);
@@ -717,7 +729,16 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
         asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
         c.vmax = s.pub_vmax; c.kstar = s.pub_kstar; thr = s.pub_thr;
       }
-      if (j < npb) {
+      doa_step = s.pub_doa != 0;        // written before the lead's bar.arrive; the lead reads its own store
+      if (doa_step) {
+        VIT_STAT(11, 1);
+        VIT_CAND_LOOP
+        if (j < npb) {
+          if (s.lpv[wp][j] == p.lt0) s.Vv[wp][VIT_HW + j] = VIT_NEG; else s.lpv[wp][j] = p.lt0;
+          s.Vu[wp][VIT_HW + j] = VIT_NEG;
+        }
+        vvb = 0.0;
+      } else if (j < npb) {
         // sources in band of this warp's destinations live in the 32-bin segments of warps w-1, w, w+1
         double seg = s.wvv[rp][warp];
         if (warp > 0) { const double x = s.wvv[rp][warp - 1]; if (x > seg) seg = x; }
@@ -735,7 +756,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     }
     prev_vmax = c.vmax;
     const int myrow = j < npb ? (int)s.rowid[j] : 0;
-    if (!sparse) vit3_append(live_v, nv, j, myrow, s.Lv[wl], &s.cnt[wl][0], lane);
+    if (!sparse && !doa_step) vit3_append(live_v, nv, j, myrow, s.Lv[wl], &s.cnt[wl][0], lane);
     vit3_append(live_u, nu, j, myrow, s.Lu[wl], &s.cnt[wl][1], lane);
     if (pf) {
       if (lane == 0) { s.nxt_nc[wp ^ 1] = nc_next; s.nxt_lpu[wp ^ 1] = nb_lpu; }
@@ -748,7 +769,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       }
     }
     vit_warp_argmax_neg(bestv, bestk);
-    if (!sparse) vvb = vit_warp_max(vvb);     // sparse: 0.0 everywhere
+    if (!sparse && !doa_step) vvb = vit_warp_max(vvb);     // sparse / dead-on-arrival: 0.0 everywhere
     const double uub = vit_warp_max(j < npb ? nu : VIT_NEG);
     if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; s.wuu[wp][warp] = uub; }
     thr_prev = thr;

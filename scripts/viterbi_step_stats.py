@@ -37,7 +37,7 @@ def main():
     steps = c[0] + c[1]
     names = ["sparse_steps", "dense_steps", "unvoiced_band_scans", "voiced_band_scans", "unvoiced_list_walks",
              "voiced_list_walks", "candidate_evaluations", "uniform_mode_steps", "dense_with_unvoiced_scan",
-             "dense_with_voiced_scan", "sparse_with_voiced_scan", "reserved11", "reserved12", "steps_with_unvoiced_band_scan", "warp_steps_dead_segment_skipped",
+             "dense_with_voiced_scan", "sparse_with_voiced_scan", "dead_on_arrival_dense_steps", "reserved12", "steps_with_unvoiced_band_scan", "warp_steps_dead_segment_skipped",
              "warp_steps_band_scanned"]
     rep = {"corpus": corpus, "utterances": n, "frames": int(fo[-1]), "steps": steps,
            "voiced_prob_eq_1_frac": float((vp == 1).float().mean()), "voiced_frac": float((vf != 0).float().mean())}

@@ -208,7 +208,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     std::vector<uint32_t> rid((size_t)npb * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) vit_pack_rows(tb.row_id.data(), npb, tb.n_rows, j, rid.data() + (size_t)j * VIT_RID_REGS);
     for (int j = 0; j < npb; ++j) { Vv[VIT_HW + j] = V[j].x; Vu[VIT_HW + j] = V[j].y; }
-    long skipped = 0, listed = 0, n_sparse = 0, n_uniform = 0, u_over = 0;
+    long skipped = 0, listed = 0, n_sparse = 0, n_uniform = 0, u_over = 0, n_doa = 0;
     bool sparse_prev = false;
     double prev_vmax = 0.0;
     for (int64_t t = 1; t < T; ++t) {
@@ -234,8 +234,13 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
       if (c.nu > VIT_LIST_MAX) ++u_over;
       for (int q = 0; q < n_cand[t]; ++q) lpv[cand_bin[(size_t)t * g.kmax + q]] = cand_lp[(size_t)t * g.kmax + q];
       const bool sparse = lp_unv[t] >= tb.lt0 + VIT_SPARSE_MARGIN;
-      if (sparse) {
-        ++n_sparse;
+      // dead-on-arrival dense step (k_viterbi.cuh): every state without a candidate observation is dead the
+      // moment it is created, only the candidate bins are evaluated
+      const double top = c.vmax + tb.lt_max;
+      const bool doa = !sparse && !getenv("ROAR_EMU_NO_DOA") && ((tb.lt0 + top) + tb.lt_max) < thr && ((lp_unv[t] + top) + tb.lt_max) < thr;
+      if (doa) ++n_doa;
+      if (sparse || doa) {
+        if (sparse) ++n_sparse;
         // candidate bins (one warp each on the device; here the "lanes" are reduced by vit_offer)
         for (int q = 0; q < n_cand[t]; ++q) {
           const int b = cand_bin[(size_t)t * g.kmax + q];
@@ -262,6 +267,11 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
             for (int q = ww * 32; q < ww * 32 + 32 && q < npb; ++q) if (c.Vv[VIT_HW + q] > seg) seg = c.Vv[VIT_HW + q];
           c.vvmax = seg;
         }
+        if (doa) {
+          if (lpv[j] == tb.lt0) Vv[(size_t)wp * VP + VIT_HW + j] = VIT_NEG;
+          Vu[(size_t)wp * VP + VIT_HW + j] = VIT_NEG;
+          continue;
+        }
         if (sparse) {
           const int w = j / 32;
           const bool uni = (int)tb.lt_uniform.size() == VIT_TW && prev_vmax <= tb.uniform_vmax && 32 * w >= 2 * VIT_HW &&
@@ -281,13 +291,13 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
         }
         if (nu + lmg >= thr) { if (cnt[wl][1] < VIT_LIST_MAX) { VitLive e; e.v = nu; e.kb = j; e.row = tb.row_id[j]; Lu[(size_t)wl * VIT_LIST_MAX + cnt[wl][1]] = e; } ++cnt[wl][1]; }
       }
-      sparse_prev = sparse;
+      sparse_prev = sparse || doa;
       prev_vmax = c.vmax;
       for (int q = 0; q < n_cand[t]; ++q) lpv[cand_bin[(size_t)t * g.kmax + q]] = tb.lt0;
     }
     const int lp_ = (int)((T - 1) & 1);
     for (int j = 0; j < npb; ++j) { V[(size_t)lp_ * npb + j].x = Vv[(size_t)lp_ * VP + VIT_HW + j]; V[(size_t)lp_ * npb + j].y = Vu[(size_t)lp_ * VP + VIT_HW + j]; }
-    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps, %ld sparse steps, %ld uniform bin-steps (uniform_vmax %g), %ld unvoiced-overflow steps of %ld\n", listed, skipped, n_sparse, n_uniform, tb.uniform_vmax, u_over, (long)T - 1);
+    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps, %ld sparse steps, %ld uniform bin-steps (uniform_vmax %g), %ld unvoiced-overflow steps, %ld dead-on-arrival dense steps of %ld\n", listed, skipped, n_sparse, n_uniform, tb.uniform_vmax, u_over, n_doa, (long)T - 1);
   } else {
   for (int64_t t = 1; t < T; ++t) {
     const cf64* Vc = V.data() + (size_t)((t - 1) & 1) * npb;
