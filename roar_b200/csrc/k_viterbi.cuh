@@ -48,6 +48,9 @@ struct VitParams {
   // of the uniform band scan, valid while vmax <= uniform_vmax (tables.hpp make_uniform_row)
   double uniform_vmax;
   double ltu[VIT_TW];
+  // smallest (same - switch) difference over the banded table entries (~ ln 99), minus a rounding margin: a voiced
+  // source whose value is below its unvoiced twin's by less than this never beats the twin at an unvoiced destination
+  double twin_gap;
 };
 
 // One DP step for pitch bin j.  V: previous values as (voiced, unvoiced) pairs; returns the new pair,
@@ -311,6 +314,7 @@ struct Vit3Step {
   const VitLive* Lu; int nu;
   double vmax; int kstar;      // first global arg-max of V[t-1]
   double vvmax;                // max over the voiced V[t-1] a destination of this warp can see in band
+  unsigned lv_mask = 0xffffffffu;   // voiced live-list entries an unvoiced destination of this warp has to visit
   bool u_dead = false;         // every unvoiced source in reach of this warp's destinations is dead (below the
                                //   liveness threshold of the step that created it): its band need not be scanned
   // tables
@@ -416,7 +420,11 @@ HD VitBest2 vit4_unvoiced_scan(const Vit3Step& c, int j, const uint32_t* rid, co
       vit_offer(bu, wb, j - VIT_HW + wd);
     }
   } else {
-    for (int e = 0; e < c.nv; ++e) vit_list_offer1(c.Lv[e], 0, c.lt2, j, 1, bu);
+#if defined(__CUDA_ARCH__)
+    for (unsigned mm = c.lv_mask; mm; mm &= mm - 1) vit_list_offer1(c.Lv[__ffs(mm) - 1], 0, c.lt2, j, 1, bu);
+#else
+    for (int e = 0; e < c.nv; ++e) if ((c.lv_mask >> e) & 1u) vit_list_offer1(c.Lv[e], 0, c.lt2, j, 1, bu);
+#endif
   }
   return bu;
 }
@@ -703,6 +711,20 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     if (sparse) {
       VitBest2 bu;
       bu.b = VIT_NEG; bu.a = 0x7fffffff;
+      if (c.nv <= VIT_LIST_MAX) {
+        // Which voiced live-list entries can matter for THIS warp's unvoiced destinations: (i) in reach of the
+        // warp's 32 bins; (ii) not dominated by their unvoiced twin -- the unvoiced state of the same bin reaches
+        // exactly the same destinations through the `same` component of the same table slot, which exceeds the
+        // `switch` component by >= twin_gap, so a voiced source with V_v - V_u < twin_gap loses strictly at every
+        // unvoiced destination.  (ii) needs the twin to be visited: only while the unvoiced band is scanned.
+        bool need = false;
+        if (lane < c.nv) {
+          const VitLive e = c.Lv[lane];
+          need = (unsigned)(e.kb - (32 * warp - VIT_HW)) <= (unsigned)(31 + 2 * VIT_HW);
+          if (need && c.nu > VIT_LIST_MAX && !c.u_dead) need = !(e.v - c.Vu[VIT_HW + e.kb] < p.twin_gap);
+        }
+        c.lv_mask = __ballot_sync(0xffffffffu, need);
+      }
       if (j < npb) {
         if (c.nv > VIT_LIST_MAX) c.vvmax = 0.0;   // (after a dense step the segment maxima would do; rare)
         // warp-uniform: every source of this warp's 32 destinations is an interior bin
@@ -757,7 +779,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     prev_vmax = c.vmax;
     const int myrow = j < npb ? (int)s.rowid[j] : 0;
     if (!sparse && !doa_step) vit3_append(live_v, nv, j, myrow, s.Lv[wl], &s.cnt[wl][0], lane);
-    vit3_append(live_u, nu, j, myrow, s.Lu[wl], &s.cnt[wl][1], lane);
+    if (!doa_step) vit3_append(live_u, nu, j, myrow, s.Lu[wl], &s.cnt[wl][1], lane);
     if (pf) {
       if (lane == 0) { s.nxt_nc[wp ^ 1] = nc_next; s.nxt_lpu[wp ^ 1] = nb_lpu; }
       if (lane < nc_next) { s.lpv[wp ^ 1][nb_bin] = nb_lp; s.cbin[wp ^ 1][lane] = (uint16_t)nb_bin; s.clp[wp ^ 1][lane] = nb_lp; }
@@ -768,9 +790,10 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
         s.lpv[wp ^ 1][b] = l; s.cbin[wp ^ 1][q] = (uint16_t)b; s.clp[wp ^ 1][q] = l;
       }
     }
-    vit_warp_argmax_neg(bestv, bestk);
+    // dead-on-arrival step: only lane 0 of a candidate warp holds a value, every unvoiced value is the sentinel
+    if (!doa_step) vit_warp_argmax_neg(bestv, bestk);
     if (!sparse && !doa_step) vvb = vit_warp_max(vvb);     // sparse / dead-on-arrival: 0.0 everywhere
-    const double uub = vit_warp_max(j < npb ? nu : VIT_NEG);
+    const double uub = doa_step ? VIT_NEG : vit_warp_max(j < npb ? nu : VIT_NEG);
     if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; s.wuu[wp][warp] = uub; }
     thr_prev = thr;
     __syncthreads();

@@ -52,7 +52,7 @@ struct roar_sup_handle {
   // K3
   double* d_lt_rows = nullptr; uint16_t* d_row_id = nullptr; double* d_freqs = nullptr;
   int n_rows = 0; double lt0 = 0, lt_max = 0, li_v = 0, li_u = 0;
-  double uniform_vmax = -1e308; double ltu[VIT_TW] = {0};
+  double uniform_vmax = -1e308; double ltu[VIT_TW] = {0}; double twin_gap = 0;
   int vit_threads = 0; size_t vit_smem = 0; int lt_in_smem = 1;
   int vit_fast = 0; size_t vit3_smem = 0;
   // K4
@@ -274,6 +274,12 @@ static int create_impl(roar_sup_handle* h, const roar_sup_config* cfg, int devic
     UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(lt_up, d_lt_rows) UP(t.row_id, d_row_id)
     UP(t.freqs, d_freqs)
     h->n_rows = t.n_rows; h->lt0 = t.lt0; h->lt_max = t.lt_max; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
+    {   // smallest same-minus-switch gap of the banded table (entries are (same, switch) pairs), less a rounding margin
+      double gap = 1e300;
+      for (size_t i = 0; i + 1 < t.lt_rows.size(); i += 2)     // (lt0, lt0) marks a destination outside the bin range
+        if (t.lt_rows[i] > t.lt0) gap = std::min(gap, t.lt_rows[i] - t.lt_rows[i + 1]);
+      h->twin_gap = (gap > 1.0 && gap < 1e299) ? gap - 1e-3 : -1e300;      // no useful gap (switch_prob ~ 0.5): the rule is off
+    }
     if (g.tw == VIT_TW && (int)t.lt_uniform.size() == VIT_TW) {
       h->uniform_vmax = t.uniform_vmax;
       for (int d = 0; d < VIT_TW; ++d) h->ltu[d] = t.lt_uniform[d];
@@ -578,7 +584,7 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
   v.cand_bin = w.cand_bin; v.cand_lp = w.cand_lp; v.n_cand = w.n_cand; v.lp_unvoiced = w.lp_unv;
   v.ptr = (uint16_t*)w.big; v.last_state = w.last_state; v.freqs = h->d_freqs; v.f0 = d_f0; v.voiced_flag = d_vflag;
   v.lt_in_smem = h->lt_in_smem; v.lt_max = h->lt_max;
-  v.uniform_vmax = h->uniform_vmax;
+  v.uniform_vmax = h->uniform_vmax; v.twin_gap = h->twin_gap;
   for (int d = 0; d < VIT_TW; ++d) v.ltu[d] = h->ltu[d];
   v.ptr_stride = 2 * g.npb; v.ptr_uoff = g.npb;
   if (h->vit_fast) {
