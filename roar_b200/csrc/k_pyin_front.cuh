@@ -44,7 +44,6 @@ struct PyinParams {
   const double* beta_cum;     // [n_thr+1]
   const double* boltz_exp;    // [kmax+1]
   const double* boltz_fact;   // [kmax+1]
-  const double* rtau;         // [max_period+1] fl(1 / tau) (optional: null = divide)
   // scratch / outputs
   float* energy;              // [max_period+1, total_frames]  E[tau] = cs[W+tau] - cs[tau] (float32 scratch, frame-contiguous)
   const int32_t* etile_off;   // [n_utts+1] prefix sum of ceil(T_i / 32): energy-kernel tiles
@@ -383,17 +382,6 @@ HD void cmnd_phase_scan2(const PyinParams& p, CmndSmem& s, int slot, int u) {
   for (int v = 0; v < u; ++v) acc += s.chunk[slot * 64 + v];
   s.chunk[slot * 64 + 32 + u] = acc;
 }
-// fl(c / tau) for an integer tau < 2^11 from r = fl(1 / tau): q0 = fl(c r), e = c - tau q0 (exact in one FMA),
-// q = fl(q0 + e r) is the correctly rounded quotient (Markstein: r is correctly rounded, tau's significand is not
-// all ones; brute-forced against the division for every tau <= 1400 x 4e5 values, 0 of 5.6e8 differ, and
-// checked with exact rational arithmetic in tests/test_hostemu.py).  Zero, subnormal-range and NaN sums take the
-// division itself.
-HD double cmnd_div_tau(double c, double dt, double r) {
-  if (!(fabs(c) > 1e-280)) return c / dt;
-  const double q0 = c * r;
-  const double e = fma(-dt, q0, c);
-  return fma(e, r, q0);
-}
 HD void cmnd_phase_emit(const PyinParams& p, const PyinTile& t, CmndSmem& s, int f, int slot, int u) {
   const int ch = cmnd_chunk(p);
   const double* d = s.Q + (size_t)f * cmnd_qs(p);
@@ -404,8 +392,7 @@ HD void cmnd_phase_emit(const PyinParams& p, const PyinTile& t, CmndSmem& s, int
   for (int i = u; i < p.n_lags; i += 32) {
     const int tau = p.min_period + i;
     const double c = ds[tau] + s.chunk[slot * 64 + 32 + (int)(((unsigned)(tau - 1) * chm) >> 20)];
-    const double mean = p.rtau ? cmnd_div_tau(c, (double)tau, ld_ro(p.rtau + tau)) : c / (double)tau;
-    out[i] = d[tau] / (mean + 2.2250738585072014e-308);
+    out[i] = d[tau] / (c / (double)tau + 2.2250738585072014e-308);
   }
 }
 

@@ -47,7 +47,7 @@ struct roar_sup_handle {
   int stft_FT = 16, stft_P = 64, stft_G = 4, stft_span = 0; size_t stft_smem = 0;
   int use_tma = 1;
   // K2
-  double *d_thr = nullptr, *d_beta = nullptr, *d_beta_cum = nullptr, *d_bexp = nullptr, *d_bfact = nullptr, *d_rtau = nullptr;
+  double *d_thr = nullptr, *d_beta = nullptr, *d_beta_cum = nullptr, *d_bexp = nullptr, *d_bfact = nullptr;
   int pyin_FT = 15, pyin_BL = 0, pyin_nb = 0, pyin_ngroups = 0, pyin_ylen = 0; size_t cmnd_smem = 0, prob_smem = 0, energy_smem = 0;
   // K3
   double* d_lt_rows = nullptr; uint16_t* d_row_id = nullptr; double* d_freqs = nullptr;
@@ -130,7 +130,7 @@ static PyinParams pyin_params_base(const roar_sup_handle* h) {
   p.npb = g.npb; p.nbps = g.nbps; p.kmax = g.kmax; p.n_thr = g.n_thr;
   p.sr = h->cfg.sample_rate; p.fmin = h->cfg.pitch_fmin; p.no_trough_prob = h->cfg.no_trough_prob;
   p.thresholds = h->d_thr; p.beta_probs = h->d_beta; p.beta_cum = h->d_beta_cum;
-  p.boltz_exp = h->d_bexp; p.boltz_fact = h->d_bfact; p.rtau = h->d_rtau;
+  p.boltz_exp = h->d_bexp; p.boltz_fact = h->d_bfact;
   return p;
 }
 
@@ -271,11 +271,6 @@ static int create_impl(roar_sup_handle* h, const roar_sup_config* cfg, int devic
     std::vector<double> lt_up = t.lt_rows;              // + one all-zero row for the fast Viterbi's sentinel sources
     lt_up.resize(lt_up.size() + 2 * (size_t)g.tw, 0.0);
     UP(t.thresholds, d_thr) UP(t.beta_probs, d_beta) UP(t.beta_cum, d_beta_cum)
-    {
-      std::vector<double> rt((size_t)g.max_period + 1, 0.0);
-      for (int tau = 1; tau <= g.max_period; ++tau) rt[tau] = 1.0 / (double)tau;
-      UP(rt, d_rtau)
-    }
     UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(lt_up, d_lt_rows) UP(t.row_id, d_row_id)
     UP(t.freqs, d_freqs)
     h->n_rows = t.n_rows; h->lt0 = t.lt0; h->lt_max = t.lt_max; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;

@@ -100,9 +100,6 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
   p.ylen = cmnd_ylen(p.FT, g.pf, g.ph, p.BL, p.nb, p.n_groups);
   p.npb = g.npb; p.nbps = g.nbps; p.kmax = g.kmax; p.n_thr = g.n_thr;
   p.sr = cfg->sample_rate; p.fmin = cfg->pitch_fmin; p.no_trough_prob = cfg->no_trough_prob;
-  std::vector<double> rtau_tab((size_t)g.max_period + 1, 0.0);
-  for (int tau = 1; tau <= g.max_period; ++tau) rtau_tab[tau] = 1.0 / (double)tau;
-  p.rtau = rtau_tab.data();
   p.thresholds = tb.thresholds.data(); p.beta_probs = tb.beta_probs.data();
   p.beta_cum = tb.beta_cum.data(); p.boltz_exp = tb.boltz_exp.data(); p.boltz_fact = tb.boltz_fact.data();
   const int64_t T = 1 + L / g.ph;
