@@ -242,7 +242,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_pyin_viterbi(const VitParams p) {
 // + 2 compare/select.
 constexpr int VIT_LIST_MAX = 32;
 constexpr int VIT_CHAINS = 1;
-constexpr int VIT_RID_REGS = (VIT_TW + 4) / 5;   // 11
 constexpr double VIT_NEG = -1e308;
 
 struct alignas(16) VitLive { double v; int32_t kb; int32_t row; };
@@ -252,19 +251,17 @@ HD void vit_offer(VitBest2& x, double s, int idx) {
   if (s > x.b || (s == x.b && idx < x.a)) { x.b = s; x.a = idx; }
 }
 
-// packed row ids of sources j-hw .. j+hw (row `zero_row` for sources outside [0, npb))
-HD void vit_pack_rows(const uint16_t* row_id, int npb, int zero_row, int j, uint32_t* rid) {
-  for (int r = 0; r < VIT_RID_REGS; ++r) rid[r] = 0;
-  for (int d = 0; d < VIT_TW; ++d) {
-    const int i = j - VIT_HW + d;
-    const uint32_t row = (i >= 0 && i < npb) ? row_id[i] : (uint32_t)zero_row;
-    rid[d / 5] |= row << (6 * (d % 5));
+// padded per-source row ids: pad[i + hw] = row of source bin i, `zero_row` for the hw sentinel sources on both sides
+HD void vit_pad_rows(const uint16_t* row_id, int npb, int zero_row, uint8_t* pad) {
+  for (int i = 0; i < npb + 2 * VIT_HW; ++i) {
+    const int b = i - VIT_HW;
+    pad[i] = (uint8_t)((b >= 0 && b < npb) ? row_id[b] : zero_row);
   }
 }
 
 // band scan over one source voicing.  Vp = &Vsrc_padded[j] (source i = j-hw+d sits at Vp[d]).
 // same/swit: best offers for the destination of the same / the other voicing; d_* = winning d.
-HD void vit_band_scan(const double* Vp, const cf64* lt2, const uint32_t* rid, double* same_b, int* same_d,
+HD void vit_band_scan(const double* Vp, const cf64* lt2, const uint8_t* rowp, double* same_b, int* same_d,
                       double* swit_b, int* swit_d) {
   // VIT_CHAINS independent running maxima over consecutive source ranges, merged in source order with
   // a strict compare: same first-index arg-max as one chain, more instruction-level parallelism
@@ -280,7 +277,7 @@ HD void vit_band_scan(const double* Vp, const cf64* lt2, const uint32_t* rid, do
       const int d = c * PER + q;
       if (d < VIT_TW) {
         const double v = Vp[d];
-        const uint32_t row = (rid[d / 5] >> (6 * (d % 5))) & 63u;
+        const uint32_t row = rowp[d];
         const cf64 e = lt2[row * VIT_TW + (2 * VIT_HW - d)];
         const double s0 = v + e.x, s1 = v + e.y;
         if (s0 > b0[c]) { b0[c] = s0; d0[c] = d; }
@@ -324,7 +321,7 @@ struct Vit3Step {
 };
 
 // new values and back-pointers of pitch bin j
-HD void vit3_step_bin(const Vit3Step& c, int j, const uint32_t* rid, double lp_v, double lp_u, double* out_v,
+HD void vit3_step_bin(const Vit3Step& c, int j, const uint8_t* rowp, double lp_v, double lp_u, double* out_v,
                       double* out_u, int* ptr_v, int* ptr_u) {
   VitBest2 bv, bu;                       // destination voiced / unvoiced
   bv.b = VIT_NEG; bv.a = 0x7fffffff; bu = bv;
@@ -336,7 +333,7 @@ HD void vit3_step_bin(const Vit3Step& c, int j, const uint32_t* rid, double lp_v
   if (c.nu > VIT_LIST_MAX) {
     if (!c.u_dead) {
       double sb, wb; int sd, wd;
-      vit_band_scan(c.Vu + j, c.lt2, rid, &sb, &sd, &wb, &wd);
+      vit_band_scan(c.Vu + j, c.lt2, rowp, &sb, &sd, &wb, &wd);
       vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
       vit_offer(bv, wb, c.npb + j - VIT_HW + wd);
     }
@@ -347,7 +344,7 @@ HD void vit3_step_bin(const Vit3Step& c, int j, const uint32_t* rid, double lp_v
     const double Wc = c.vvmax + c.lt_max;
     if (!(bv.b > Wc && bu.b > Wc)) {
       double sb, wb; int sd, wd;
-      vit_band_scan(c.Vv + j, c.lt2, rid, &sb, &sd, &wb, &wd);
+      vit_band_scan(c.Vv + j, c.lt2, rowp, &sb, &sd, &wb, &wd);
       vit_offer(bv, sb, j - VIT_HW + sd);
       vit_offer(bu, wb, j - VIT_HW + wd);
     }
@@ -360,13 +357,13 @@ HD void vit3_step_bin(const Vit3Step& c, int j, const uint32_t* rid, double lp_v
 
 // light band scan: one table component (COMP 0 = same voicing, 1 = switch) -> one destination
 template <int COMP>
-HD void vit_band_scan1(const double* Vp, const cf64* lt2, const uint32_t* rid, double* best, int* best_d) {
+HD void vit_band_scan1(const double* Vp, const cf64* lt2, const uint8_t* rowp, double* best, int* best_d) {
   double b = VIT_NEG;
   int bd = 0;
 #pragma unroll
   for (int d = 0; d < VIT_TW; ++d) {
     const double v = Vp[d];
-    const uint32_t row = (rid[d / 5] >> (6 * (d % 5))) & 63u;
+    const uint32_t row = rowp[d];
     const double* e = reinterpret_cast<const double*>(lt2 + row * VIT_TW + (2 * VIT_HW - d));
     const double s0 = v + e[COMP];
     if (s0 > b) { b = s0; bd = d; }
@@ -399,14 +396,14 @@ HD void vit_list_offer1(const VitLive& e, int state_base, const cf64* lt2, int j
 // (it needs nothing but the previous rows and lists, so it runs while one warp still reduces the global
 // arg-max); part B adds the out-of-band offer of k*.  vit_offer breaks ties by state index, so the
 // order in which offers arrive does not matter.
-HD VitBest2 vit4_unvoiced_scan(const Vit3Step& c, int j, const uint32_t* rid, const double* uniform_row) {
+HD VitBest2 vit4_unvoiced_scan(const Vit3Step& c, int j, const uint8_t* rowp, const double* uniform_row) {
   VitBest2 bu;
   bu.b = VIT_NEG; bu.a = 0x7fffffff;
   if (c.nu > VIT_LIST_MAX) {
     if (!c.u_dead) {
       double sb; int sd;
       if (uniform_row) vit_band_scan1u(c.Vu + j, uniform_row, &sb, &sd);
-      else vit_band_scan1<0>(c.Vu + j, c.lt2, rid, &sb, &sd);
+      else vit_band_scan1<0>(c.Vu + j, c.lt2, rowp, &sb, &sd);
       vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
     }
   } else {
@@ -416,7 +413,7 @@ HD VitBest2 vit4_unvoiced_scan(const Vit3Step& c, int j, const uint32_t* rid, co
     const double Wc = c.vvmax + c.lt_max;
     if (!(bu.b > Wc)) {
       double wb; int wd;
-      vit_band_scan1<1>(c.Vv + j, c.lt2, rid, &wb, &wd);
+      vit_band_scan1<1>(c.Vv + j, c.lt2, rowp, &wb, &wd);
       vit_offer(bu, wb, j - VIT_HW + wd);
     }
   } else {
@@ -540,6 +537,7 @@ struct alignas(16) Vit3Shared {
   int nxt_nc[2];                             //   (written one step ahead by the prefetch warp)
   uint16_t cbin[2][VIT_KMAX_MAX];
   uint16_t rowid[VIT_NPB_MAX];
+  uint8_t rowpad[VIT_VP_MAX + 6];            // row id per padded source position (generic band scans)
 };
 
 // warp-aggregated append of the live states of one voicing
@@ -604,8 +602,11 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     if (tid < 6) (&s.cnt[0][0])[tid] = tid < 2 ? VIT_LIST_MAX + 1 : 0;   // time 0: scan everything
   }
   const int j = tid;
-  uint32_t rid[VIT_RID_REGS];
-  vit_pack_rows(p.row_id, npb, zero_row, j < npb ? j : 0, rid);
+  for (int i = tid; i < npb + 2 * VIT_HW; i += nthr) {
+    const int b = i - VIT_HW;
+    s.rowpad[i] = (uint8_t)((b >= 0 && b < npb) ? p.row_id[b] : zero_row);
+  }
+  const uint8_t* rid = s.rowpad + (j < npb ? j : 0);
   __syncthreads();
   // frame 0 observations
   int nc_cur = p.n_cand[f0];

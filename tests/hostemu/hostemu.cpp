@@ -205,8 +205,8 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     for (size_t i = (size_t)tb.n_rows * VIT_TW; i < lt2.size(); ++i) { lt2[i].x = 0; lt2[i].y = 0; }
     std::vector<VitLive> Lv(3 * VIT_LIST_MAX), Lu(3 * VIT_LIST_MAX);
     int cnt[3][2] = {{VIT_LIST_MAX + 1, VIT_LIST_MAX + 1}, {0, 0}, {0, 0}};
-    std::vector<uint32_t> rid((size_t)npb * VIT_RID_REGS);
-    for (int j = 0; j < npb; ++j) vit_pack_rows(tb.row_id.data(), npb, tb.n_rows, j, rid.data() + (size_t)j * VIT_RID_REGS);
+    std::vector<uint8_t> rid((size_t)npb + 2 * VIT_HW);
+    vit_pad_rows(tb.row_id.data(), npb, tb.n_rows, rid.data());
     for (int j = 0; j < npb; ++j) { Vv[VIT_HW + j] = V[j].x; Vu[VIT_HW + j] = V[j].y; }
     long skipped = 0, listed = 0, n_sparse = 0, n_uniform = 0, u_over = 0, n_doa = 0;
     bool sparse_prev = false;
@@ -278,13 +278,13 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
                            32 * w + 31 + 2 * VIT_HW <= npb - 1;
           if (uni) ++n_uniform;
           if (c.nv > VIT_LIST_MAX) c.vvmax = 0.0;
-          const VitBest2 bu = vit4_unvoiced_scan(c, j, rid.data() + (size_t)j * VIT_RID_REGS, uni ? tb.lt_uniform.data() : nullptr);
+          const VitBest2 bu = vit4_unvoiced_scan(c, j, rid.data() + j, uni ? tb.lt_uniform.data() : nullptr);
           vit4_unvoiced_finish(bu, npb, tb.lt0, c.vmax, c.kstar, j, lp_unv[t], &nu, &au);
           if (lpv[j] == tb.lt0) Vv[(size_t)wp * VP + VIT_HW + j] = VIT_NEG;
           Vu[(size_t)wp * VP + VIT_HW + j] = nu;
           ptr[(size_t)t * 2 * npb + npb + j] = (uint16_t)au;
         } else {
-          vit3_step_bin(c, j, rid.data() + (size_t)j * VIT_RID_REGS, lpv[j], lp_unv[t], &nv, &nu, &av, &au);
+          vit3_step_bin(c, j, rid.data() + j, lpv[j], lp_unv[t], &nv, &nu, &av, &au);
           Vv[(size_t)wp * VP + VIT_HW + j] = nv; Vu[(size_t)wp * VP + VIT_HW + j] = nu;
           ptr[(size_t)t * 2 * npb + j] = (uint16_t)av; ptr[(size_t)t * 2 * npb + npb + j] = (uint16_t)au;
           if (nv + lmg >= thr) { if (cnt[wl][0] < VIT_LIST_MAX) { VitLive e; e.v = nv; e.kb = j; e.row = tb.row_id[j]; Lv[(size_t)wl * VIT_LIST_MAX + cnt[wl][0]] = e; } ++cnt[wl][0]; }
