@@ -112,7 +112,14 @@ __global__ void __launch_bounds__(256) k_align_prior_interp(const PriorInterpPar
   }
 }
 
+// The float32 log-probability of prior_logp32 splits into a column term lc(k), a row term lb2(y) and the mixed
+// term lb1(k, y); each is a self-contained sub-expression of the reference's formula, so evaluating lc once per
+// column and lb2 once per row (shared memory) and only lb1 per element gives bit-identical values with a third of
+// the table look-ups and conversions.  Elements are walked with incremental (row, column) indices: no division.
+constexpr int PRIOR_MAX_N = 2048;      // columns staged in shared memory (longer texts: the per-element path)
 __global__ void __launch_bounds__(256) k_align_prior(const PriorParams p) {
+  __shared__ float s_lc[PRIOR_MAX_N];
+  __shared__ float s_lb2[64];
   const int utt = p.utt_base + blockIdx.y;
   const int N = p.text_len[utt], M = p.mel_len[utt];
   const int r0 = blockIdx.x * p.rows_per_cta;
@@ -121,9 +128,33 @@ __global__ void __launch_bounds__(256) k_align_prior(const PriorParams p) {
   float* out = p.out + p.out_off[utt];
   const int64_t e0 = (int64_t)r0 * N, e1 = (int64_t)r1 * N;
   const bool integer = p.scaling == 1.0;
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-    const int m = (int)(e / N), k = (int)(e - (int64_t)m * N);
-    out[e] = integer ? prior_value_int(p, N, M, m + 1, k) : prior_value_real(p, N, M, m + 1, k);
+  if (!integer || N > PRIOR_MAX_N || p.rows_per_cta > 64) {
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+      const int m = (int)(e / N), k = (int)(e - (int64_t)m * N);
+      out[e] = integer ? prior_value_int(p, N, M, m + 1, k) : prior_value_real(p, N, M, m + 1, k);
+    }
+    return;
+  }
+  const int n = N - 1;
+  for (int k = threadIdx.x; k < N; k += blockDim.x)
+    s_lc[k] = prior_sub32(prior_sub32(prior_g32(p, n + 1), prior_g32(p, k + 1)), prior_g32(p, n - k + 1));
+  for (int r = threadIdx.x; r < r1 - r0; r += blockDim.x) {
+    const int y = r0 + r + 1;
+    s_lb2[r] = prior_sub32(prior_add32(prior_g32(p, y), prior_g32(p, M + 1 - y)), prior_g32(p, M + 1));
+  }
+  __syncthreads();
+  const float g_nm = prior_g32(p, n + M + 1);
+  // thread's first element and its stride in (row, column) form
+  int row = (int)threadIdx.x / N, k = (int)threadIdx.x - row * N;
+  const int drow = (int)blockDim.x / N, dk = (int)blockDim.x - drow * N;
+  const int rows = r1 - r0;
+  while (row < rows) {
+    const int y = r0 + row + 1;
+    const float lb1 = prior_sub32(prior_add32(prior_g32(p, k + y), prior_g32(p, n - k + M + 1 - y)), g_nm);
+    const float lp = prior_sub32(prior_add32(s_lc[k], lb1), s_lb2[row]);
+    out[e0 + (int64_t)row * N + k] = (float)exp((double)lp);
+    row += drow; k += dk;
+    if (k >= N) { k -= N; ++row; }
   }
 }
 
