@@ -298,8 +298,21 @@ def test_prior_vs_float64_and_scaling(ex):
     assert np.abs(got[ref > 1e-30] / ref[ref > 1e-30] - 1).max() < 1e-5
 
 
+def test_prior_long_text_takes_the_per_element_path(ex):
+    """k_align_prior stages the column term of texts up to 2048 tokens in shared memory; longer ones take the
+    per-element evaluation.  Both must give the reference's float32 values (bit-equal: same operations)."""
+    from oracle import prior as oprior
+    for n, m in [(2048, 2300), (2049, 2300), (3, 5)]:
+        out, oo = ex.align_prior([n], [m])
+        got = out[oo[0]:oo[1]].view(m, n).cpu().numpy()
+        ref32 = oprior.beta_binomial_prior_distribution(n, m)
+        assert np.array_equal(got.argmax(1), ref32.argmax(1))
+        np.testing.assert_allclose(got, ref32, rtol=2e-6, atol=1e-30)
+
+
 @pytest.mark.parametrize("kw,okw", [
     (dict(pyin_win_length=600), dict(win_length=600)),
+    (dict(pyin_hop_length=250), dict(hop_length=250)),      # hop % 4 != 0: scalar staging of the energy kernel
     (dict(pyin_hop_length=128), dict(hop_length=128)),
     (dict(pyin_win_length=384, pyin_hop_length=128), dict(win_length=384, hop_length=128)),
 ])
