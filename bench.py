@@ -700,6 +700,18 @@ def main():
                 "note": "SURVEY.md 8d: frac = max(algorithmic bytes / HBM peak, algorithmic flops / FP peak); flops are the "
                         "cheapest standard algorithm's (FFT-form CMND, banded Viterbi), the kernels execute more (direct "
                         "float64 autocorrelation) -- the chain is CUDA-core issue / FP64-pipe bound, not HBM bound"}
+    fp64_file = os.path.join(ROOT, "profiles", "r2_fp64_peak.json")
+    if os.path.exists(fp64_file):      # measured FP64 peak of this GPU model (micro-benchmark): what bounds K2a's direct autocorrelation
+        with open(fp64_file) as f:
+            fp64 = json.load(f)
+        # executed DFMA of the direct block autocorrelation: one block of `hop` samples per frame plus one per 15-frame
+        # tile, (max_period + 1) lags rounded up to 11 per lane
+        lags_exec = -(-(ex.max_period + 1) // 11) * 11
+        executed = (2.0 * (frames * 16.0 / 15.0 + 0.5 * n_utts) * lags_exec * scfg.pyin_hop
+                    if scfg.pyin_frame == 4 * scfg.pyin_hop else None)
+        roofline["fp64"] = {"peak_tflops_measured": fp64["dfma_tflops"], "peak_source": "profiles/r2_fp64_peak.json (" + fp64["source"] + ")",
+                            "k_pyin_cmnd_executed_tflops": (executed / (per.get("pyin_cmnd", 0.0) * 1e-3) / 1e12) if executed and per.get("pyin_cmnd") else None,
+                            "note": "executed (not algorithmic) float64 multiply-adds of the direct block autocorrelation over the kernel time"}
     roofline_kernels = {}
     for k, b in alg.items():
         if per.get(k, 0) > 0:
