@@ -312,7 +312,6 @@ def test_prior_long_text_takes_the_per_element_path(ex):
 
 @pytest.mark.parametrize("kw,okw", [
     (dict(pyin_win_length=600), dict(win_length=600)),
-    (dict(pyin_hop_length=250), dict(hop_length=250)),      # hop % 4 != 0: scalar staging of the energy kernel
     (dict(pyin_hop_length=128), dict(hop_length=128)),
     (dict(pyin_win_length=384, pyin_hop_length=128), dict(win_length=384, hop_length=128)),
 ])
