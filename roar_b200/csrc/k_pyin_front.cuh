@@ -733,10 +733,19 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
         if (p.n_thr <= 128) {
           // thresholds where some active trough starts (hist != 0) as a bit mask; between two of them K is
           // constant, so the inner loop is just  acc += K * beta[c]  (same additions, same order)
-          unsigned nzm[4];
-#pragma unroll
-          for (int w = 0; w < 4; ++w) nzm[w] = __ballot_sync(0xffffffffu, 32 * w + lane < p.n_thr && hist[32 * w + lane] != 0);
-          int c = cmin;
+          // the remaining change points as four warp-uniform words, popped lowest bit first
+          unsigned rem0 = __ballot_sync(0xffffffffu, lane < p.n_thr && hist[lane] != 0);
+          unsigned rem1 = __ballot_sync(0xffffffffu, 32 + lane < p.n_thr && hist[32 + lane] != 0);
+          unsigned rem2 = __ballot_sync(0xffffffffu, 64 + lane < p.n_thr && hist[64 + lane] != 0);
+          unsigned rem3 = __ballot_sync(0xffffffffu, 96 + lane < p.n_thr && hist[96 + lane] != 0);
+#define PROB_POP_CP(dst)                                                              \
+          if (rem0) { dst = __ffs(rem0) - 1; rem0 &= rem0 - 1; }                       \
+          else if (rem1) { dst = 31 + __ffs(rem1); rem1 &= rem1 - 1; }                 \
+          else if (rem2) { dst = 63 + __ffs(rem2); rem2 &= rem2 - 1; }                 \
+          else if (rem3) { dst = 95 + __ffs(rem3); rem3 &= rem3 - 1; }                 \
+          else dst = p.n_thr;
+          int c;
+          PROB_POP_CP(c)
           while (c < p.n_thr) {
             {   // change point c
               const unsigned m = __ballot_sync(0xffffffffu, cr == c);
@@ -746,17 +755,13 @@ __global__ void __launch_bounds__(256) k_pyin_probs(const PyinParams p) {
               if (more && lane == 0 && m) carry[c] = cy + __popc(m);
               K = bfact[n] * bexp[pos];
             }
-            int cn = p.n_thr;       // next change point
-#pragma unroll
-            for (int w = 3; w >= 0; --w) {
-              unsigned mw = nzm[w];
-              if (c >= 32 * w) mw = c >= 32 * w + 31 ? 0u : mw & (0xfffffffeu << (c - 32 * w));
-              if (mw) cn = 32 * w + __ffs(mw) - 1;
-            }
+            int cn;
+            PROB_POP_CP(cn)
             int cc = c > cr ? c : cr;
             for (; cc < cn; ++cc) acc += K * beta[cc];
             c = cn;
           }
+#undef PROB_POP_CP
         } else {
           for (int c = cmin; c < p.n_thr; ++c) {
             const int hc = hist[c];      // warp-uniform
