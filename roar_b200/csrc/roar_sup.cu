@@ -274,12 +274,7 @@ static int create_impl(roar_sup_handle* h, const roar_sup_config* cfg, int devic
     UP(t.boltz_exp, d_bexp) UP(t.boltz_fact, d_bfact) UP(lt_up, d_lt_rows) UP(t.row_id, d_row_id)
     UP(t.freqs, d_freqs)
     h->n_rows = t.n_rows; h->lt0 = t.lt0; h->lt_max = t.lt_max; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
-    {   // smallest same-minus-switch gap of the banded table (entries are (same, switch) pairs), less a rounding margin
-      double gap = 1e300;
-      for (size_t i = 0; i + 1 < t.lt_rows.size(); i += 2)     // (lt0, lt0) marks a destination outside the bin range
-        if (t.lt_rows[i] > t.lt0) gap = std::min(gap, t.lt_rows[i] - t.lt_rows[i + 1]);
-      h->twin_gap = (gap > 1.0 && gap < 1e299) ? gap - 1e-3 : -1e300;      // no useful gap (switch_prob ~ 0.5): the rule is off
-    }
+    h->twin_gap = t.twin_gap;
     if (g.tw == VIT_TW && (int)t.lt_uniform.size() == VIT_TW) {
       h->uniform_vmax = t.uniform_vmax;
       for (int d = 0; d < VIT_TW; ++d) h->ltu[d] = t.lt_uniform[d];

@@ -241,6 +241,7 @@ struct PyinTables {
   int n_rows = 0;
   double lt0 = 0;                   // log(0 + tiny): every out-of-band transition
   double lt_max = 0;                // largest entry of lt_rows
+  double twin_gap = -1e300;         // smallest (same - switch) entry difference minus a rounding margin (k_viterbi.cuh rule 8); -1e300: rule off
   // interior rows (source bins hw .. npb-1-hw) differ only by the rounding of the row sum (a last-place
   // unit in a few entries).  fl(V + lt) does not see that difference once |V| >= 2^uniform_emin (see
   // make_uniform_row): then every interior source may use `lt_uniform` (the same-voicing entries of one
@@ -388,6 +389,12 @@ inline PyinTables make_pyin_tables(const roar_sup_config& c, const Geometry& g) 
   t.n_rows = (int)seen.size();
   t.lt_max = t.lt0;
   for (double v : t.lt_rows) if (v > t.lt_max) t.lt_max = v;
+  {   // (lt0, lt0) marks a destination outside the bin range: never offered
+    double gap = 1e300;
+    for (size_t i = 0; i + 1 < t.lt_rows.size(); i += 2)
+      if (t.lt_rows[i] > t.lt0) gap = std::min(gap, t.lt_rows[i] - t.lt_rows[i + 1]);
+    t.twin_gap = (gap > 1.0 && gap < 1e299) ? gap - 1e-3 : -1e300;
+  }
   t.li_voiced = std::log(0.0 + kTiny64);
   t.li_unvoiced = std::log(1.0 / n + kTiny64);
   make_uniform_row(t, g);

@@ -278,6 +278,17 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
                            32 * w + 31 + 2 * VIT_HW <= npb - 1;
           if (uni) ++n_uniform;
           if (c.nv > VIT_LIST_MAX) c.vvmax = 0.0;
+          // the kernel's per-warp filter of the voiced live list (reach of the warp's 32 bins, twin dominance)
+          c.lv_mask = 0xffffffffu;
+          if (c.nv <= VIT_LIST_MAX && !getenv("ROAR_EMU_NO_TWIN")) {
+            c.lv_mask = 0;
+            for (int e = 0; e < c.nv; ++e) {
+              const VitLive& le = c.Lv[e];
+              bool need = (unsigned)(le.kb - (32 * w - VIT_HW)) <= (unsigned)(31 + 2 * VIT_HW);
+              if (need && c.nu > VIT_LIST_MAX) need = !(le.v - c.Vu[VIT_HW + le.kb] < tb.twin_gap);
+              if (need) c.lv_mask |= 1u << e;
+            }
+          }
           const VitBest2 bu = vit4_unvoiced_scan(c, j, rid.data() + j, uni ? tb.lt_uniform.data() : nullptr);
           vit4_unvoiced_finish(bu, npb, tb.lt0, c.vmax, c.kstar, j, lp_unv[t], &nu, &au);
           if (lpv[j] == tb.lt0) Vv[(size_t)wp * VP + VIT_HW + j] = VIT_NEG;
