@@ -51,6 +51,9 @@ struct VitParams {
   // smallest (same - switch) difference over the banded table entries (~ ln 99), minus a rounding margin: a voiced
   // source whose value is below its unvoiced twin's by less than this never beats the twin at an unvoiced destination
   double twin_gap;
+  // 1 when the centre entry of the uniform row is its strict maximum by > 1e-3 (tables.hpp): a warp whose sources in
+  // reach all hold the same unvoiced value X >= -1e12 then knows its band-scan result without scanning (rule 10)
+  int32_t flat_ok;
 };
 
 // One DP step for pitch bin j.  V: previous values as (voiced, unvoiced) pairs; returns the new pair,
@@ -311,6 +314,7 @@ struct Vit3Step {
   const VitLive* Lu; int nu;
   double vmax; int kstar;      // first global arg-max of V[t-1]
   double vvmax;                // max over the voiced V[t-1] a destination of this warp can see in band
+  bool u_flat = false; double u_flat_val = 0.0;   // every unvoiced source in reach of this warp holds exactly this value
   unsigned lv_mask = 0xffffffffu;   // voiced live-list entries an unvoiced destination of this warp has to visit
   bool u_dead = false;         // every unvoiced source in reach of this warp's destinations is dead (below the
                                //   liveness threshold of the step that created it): its band need not be scanned
@@ -402,7 +406,8 @@ HD VitBest2 vit4_unvoiced_scan(const Vit3Step& c, int j, const uint8_t* rowp, co
   if (c.nu > VIT_LIST_MAX) {
     if (!c.u_dead) {
       double sb; int sd;
-      if (uniform_row) vit_band_scan1u(c.Vu + j, uniform_row, &sb, &sd);
+      if (uniform_row && c.u_flat) { sb = c.u_flat_val + uniform_row[VIT_HW]; sd = VIT_HW; }   // rule 10: the centre tap wins
+      else if (uniform_row) vit_band_scan1u(c.Vu + j, uniform_row, &sb, &sd);
       else vit_band_scan1<0>(c.Vu + j, c.lt2, rowp, &sb, &sd);
       vit_offer(bu, sb, c.npb + j - VIT_HW + sd);
     }
@@ -504,6 +509,13 @@ __device__ __forceinline__ double vit_warp_max(double v) {
   const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
   return __hiloint2double((int)mhi, (int)mlo);
 }
+// minimum of negative finite doubles: smaller value <=> larger (hi, lo) bit pattern
+__device__ __forceinline__ double vit_warp_min(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  return __hiloint2double((int)mhi, (int)mlo);
+}
 // (max value, smallest index attaining it)
 __device__ __forceinline__ void vit_warp_argmax_neg(double& v, int& k) {
   const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
@@ -529,6 +541,7 @@ struct alignas(16) Vit3Shared {
   VitLive Lu[3][VIT_LIST_MAX];
   double wv[2][32], wvv[2][32];              // per-warp partials (= 32-bin segment stats)
   double wuu[2][32];                         // maximum of the segment's unvoiced values (dead-segment rule)
+  double wul[2][32];                         // minimum of the segment's unvoiced values (flat-segment rule)
   int wk[2][32];
   int cnt[3][2];
   int pub_kstar, pub_doa;                    // pub_doa: dead-on-arrival dense step (see the kernel)
@@ -632,7 +645,7 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
   }
   vit_warp_argmax_neg(bestv, bestk);
   vvb = vit_warp_max(vvb);
-  if (lane == 0) { s.wv[0][warp] = bestv; s.wk[0][warp] = bestk; s.wvv[0][warp] = vvb; s.wuu[0][warp] = 0.0; }   // 0.0: no bound yet
+  if (lane == 0) { s.wv[0][warp] = bestv; s.wk[0][warp] = bestk; s.wvv[0][warp] = vvb; s.wuu[0][warp] = 0.0; s.wul[0][warp] = VIT_NEG; }   // 0.0: no bound yet (and not flat)
   __syncthreads();
 
   // One warp (`lead`, an interior one) reduces the block-wide quantities of a step -- first global
@@ -661,6 +674,16 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
       if (warp > 0) { const double x = s.wuu[rp][warp - 1]; segu = x > segu ? x : segu; }
       if (warp + 1 < nwarp) { const double x = s.wuu[rp][warp + 1]; segu = x > segu ? x : segu; }
       c.u_dead = segu + p.lt_max < thr_prev;
+      // FLAT SEGMENTS (rule 10).  When the three segments in reach hold one and the same unvoiced value X (min ==
+      // max, bitwise), every in-band offer to a destination of this warp is fl(X + row[d]) with the uniform row:
+      // the largest is the centre tap's (strict row maximum by > 1e-3, far above an ulp of X >= -1e12), attained
+      // there only -- value fl(X + row[hw]), arg-max the destination's own bin, exactly what the scan returns.
+      // Far from the pitch track the unvoiced layer evolves identically in every bin, so this is the common case
+      // (~45 % of the uniform band scans on the bench corpus).
+      const double x = s.wuu[rp][warp];
+      bool flat = p.flat_ok && warp > 0 && warp + 1 < nwarp && x == s.wul[rp][warp] && x >= -1e12;
+      if (flat) flat = s.wuu[rp][warp - 1] == x && s.wul[rp][warp - 1] == x && s.wuu[rp][warp + 1] == x && s.wul[rp][warp + 1] == x;
+      c.u_flat = flat; c.u_flat_val = x;
     }
     VIT_STAT(13, (c.nu > VIT_LIST_MAX) ? 1 : 0);
 #ifdef ROAR_VIT_STATS
@@ -795,7 +818,9 @@ __global__ void __launch_bounds__(608, 2) k_pyin_viterbi51(const VitParams p) {
     if (!doa_step) vit_warp_argmax_neg(bestv, bestk);
     if (!sparse && !doa_step) vvb = vit_warp_max(vvb);     // sparse / dead-on-arrival: 0.0 everywhere
     const double uub = doa_step ? VIT_NEG : vit_warp_max(j < npb ? nu : VIT_NEG);
-    if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; s.wuu[wp][warp] = uub; }
+    // segment minimum (flat-segment rule); lanes beyond the last bin hold the maximum so that they never decide
+    const double ulb = doa_step ? VIT_NEG : vit_warp_min(j < npb ? nu : uub);
+    if (lane == 0) { s.wv[wp][warp] = bestv; s.wk[wp][warp] = bestk; s.wvv[wp][warp] = vvb; s.wuu[wp][warp] = uub; s.wul[wp][warp] = ulb; }
     thr_prev = thr;
     __syncthreads();
   }

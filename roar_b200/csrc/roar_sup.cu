@@ -52,7 +52,7 @@ struct roar_sup_handle {
   // K3
   double* d_lt_rows = nullptr; uint16_t* d_row_id = nullptr; double* d_freqs = nullptr;
   int n_rows = 0; double lt0 = 0, lt_max = 0, li_v = 0, li_u = 0;
-  double uniform_vmax = -1e308; double ltu[VIT_TW] = {0}; double twin_gap = 0;
+  double uniform_vmax = -1e308; double ltu[VIT_TW] = {0}; double twin_gap = 0; int flat_ok = 0;
   int vit_threads = 0; size_t vit_smem = 0; int lt_in_smem = 1;
   int vit_fast = 0; size_t vit3_smem = 0;
   // K4
@@ -275,6 +275,7 @@ static int create_impl(roar_sup_handle* h, const roar_sup_config* cfg, int devic
     UP(t.freqs, d_freqs)
     h->n_rows = t.n_rows; h->lt0 = t.lt0; h->lt_max = t.lt_max; h->li_v = t.li_voiced; h->li_u = t.li_unvoiced;
     h->twin_gap = t.twin_gap;
+    { const char* env_f = getenv("ROAR_SUP_NO_FLAT"); h->flat_ok = (env_f && env_f[0] == '1') ? 0 : t.flat_ok; }
     if (g.tw == VIT_TW && (int)t.lt_uniform.size() == VIT_TW) {
       h->uniform_vmax = t.uniform_vmax;
       for (int d = 0; d < VIT_TW; ++d) h->ltu[d] = t.lt_uniform[d];
@@ -579,7 +580,7 @@ int roar_sup_pyin(roar_sup_handle* h, const float* d_audio, const int64_t* d_sam
   v.cand_bin = w.cand_bin; v.cand_lp = w.cand_lp; v.n_cand = w.n_cand; v.lp_unvoiced = w.lp_unv;
   v.ptr = (uint16_t*)w.big; v.last_state = w.last_state; v.freqs = h->d_freqs; v.f0 = d_f0; v.voiced_flag = d_vflag;
   v.lt_in_smem = h->lt_in_smem; v.lt_max = h->lt_max;
-  v.uniform_vmax = h->uniform_vmax; v.twin_gap = h->twin_gap;
+  v.uniform_vmax = h->uniform_vmax; v.twin_gap = h->twin_gap; v.flat_ok = h->flat_ok;
   for (int d = 0; d < VIT_TW; ++d) v.ltu[d] = h->ltu[d];
   v.ptr_stride = 2 * g.npb; v.ptr_uoff = g.npb;
   if (h->vit_fast) {

@@ -241,6 +241,7 @@ struct PyinTables {
   int n_rows = 0;
   double lt0 = 0;                   // log(0 + tiny): every out-of-band transition
   double lt_max = 0;                // largest entry of lt_rows
+  int flat_ok = 0;                  // centre entry of the uniform row is its strict maximum by > 1e-3 (k_viterbi.cuh rule 10)
   double twin_gap = -1e300;         // smallest (same - switch) entry difference minus a rounding margin (k_viterbi.cuh rule 8); -1e300: rule off
   // interior rows (source bins hw .. npb-1-hw) differ only by the rounding of the row sum (a last-place
   // unit in a few entries).  fl(V + lt) does not see that difference once |V| >= 2^uniform_emin (see
@@ -308,6 +309,9 @@ inline void make_uniform_row(PyinTables& t, const Geometry& g) {
   t.lt_uniform.resize(tw);
   for (int d = 0; d < tw; ++d) t.lt_uniform[d] = t.lt_rows[((size_t)base * tw + d) * 2];
   t.uniform_vmax = emin <= -1074 ? 0.0 : -std::ldexp(1.0, emin);
+  t.flat_ok = 1;
+  for (int d = 0; d < tw; ++d)
+    if (d != hw && !(t.lt_uniform[hw] - t.lt_uniform[d] > 1e-3)) t.flat_ok = 0;
 }
 
 inline PyinTables make_pyin_tables(const roar_sup_config& c, const Geometry& g) {

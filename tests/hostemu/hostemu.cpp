@@ -208,7 +208,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     std::vector<uint8_t> rid((size_t)npb + 2 * VIT_HW);
     vit_pad_rows(tb.row_id.data(), npb, tb.n_rows, rid.data());
     for (int j = 0; j < npb; ++j) { Vv[VIT_HW + j] = V[j].x; Vu[VIT_HW + j] = V[j].y; }
-    long skipped = 0, listed = 0, n_sparse = 0, n_uniform = 0, u_over = 0, n_doa = 0;
+    long skipped = 0, listed = 0, n_sparse = 0, n_uniform = 0, u_over = 0, n_doa = 0, n_flat = 0;
     bool sparse_prev = false;
     double prev_vmax = 0.0;
     for (int64_t t = 1; t < T; ++t) {
@@ -289,6 +289,16 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
               if (need) c.lv_mask |= 1u << e;
             }
           }
+          // flat-segment rule: the three 32-bin segments in reach hold one unvoiced value
+          c.u_flat = false;
+          if (uni && tb.flat_ok && !getenv("ROAR_EMU_NO_FLAT")) {
+            const double x0 = c.Vu[VIT_HW + 32 * w];
+            bool flat = x0 >= -1e12;
+            for (int q2 = 32 * (w - 1); flat && q2 < 32 * (w + 2); ++q2)
+              if (q2 >= 0 && q2 < npb && c.Vu[VIT_HW + q2] != x0) flat = false;
+            c.u_flat = flat; c.u_flat_val = x0;
+            if (flat && c.nu > VIT_LIST_MAX) ++n_flat;
+          }
           const VitBest2 bu = vit4_unvoiced_scan(c, j, rid.data() + j, uni ? tb.lt_uniform.data() : nullptr);
           vit4_unvoiced_finish(bu, npb, tb.lt0, c.vmax, c.kstar, j, lp_unv[t], &nu, &au);
           if (lpv[j] == tb.lt0) Vv[(size_t)wp * VP + VIT_HW + j] = VIT_NEG;
@@ -308,7 +318,7 @@ int emu_pyin(const roar_sup_config* cfg, const float* audio, int64_t L, float* f
     }
     const int lp_ = (int)((T - 1) & 1);
     for (int j = 0; j < npb; ++j) { V[(size_t)lp_ * npb + j].x = Vv[(size_t)lp_ * VP + VIT_HW + j]; V[(size_t)lp_ * npb + j].y = Vu[(size_t)lp_ * VP + VIT_HW + j]; }
-    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps, %ld sparse steps, %ld uniform bin-steps (uniform_vmax %g), %ld unvoiced-overflow steps, %ld dead-on-arrival dense steps of %ld\n", listed, skipped, n_sparse, n_uniform, tb.uniform_vmax, u_over, n_doa, (long)T - 1);
+    if (getenv("ROAR_EMU_VERBOSE")) fprintf(stderr, "viterbi fast: %ld list steps, %ld overflow steps, %ld sparse steps, %ld uniform bin-steps (uniform_vmax %g), %ld unvoiced-overflow steps, %ld dead-on-arrival dense steps of %ld, %ld flat bin-scans\n", listed, skipped, n_sparse, n_uniform, tb.uniform_vmax, u_over, n_doa, (long)T - 1, n_flat);
   } else {
   for (int64_t t = 1; t < T; ++t) {
     const cf64* Vc = V.data() + (size_t)((t - 1) & 1) * npb;

@@ -125,7 +125,8 @@ def test_emu_viterbi_fast_path_equals_generic(monkeypatch):
 
 
 def test_emu_viterbi_round2_rules_are_exact(monkeypatch):
-    """Dead-on-arrival dense steps and the twin filter of the voiced live list (k_viterbi.cuh rules 7, 8) only
+    """Dead-on-arrival dense steps, the twin filter of the voiced live list and the flat-segment shortcut
+    (k_viterbi.cuh rules 7, 8, 10) only
     skip work that cannot reach the decoded path: switching either off, or both, or taking the every-source
     recursion gives the same states.  PCM-quantised audio with clipped voiced probability (many dense steps)."""
     cfg = SupConfig(highfreq=8000.0)
@@ -133,11 +134,12 @@ def test_emu_viterbi_round2_rules_are_exact(monkeypatch):
     for u in man[:2]:
         y = synth.synth_utterance(synth.CORPORA["C2"]["seed"], u.utt_id, min(u.n_samples, 40000), 22050, u.speaker)
         y = (np.clip(np.round(y * 32767), -32768, 32767) / 32768.0).astype(np.float32)
-        for k in ("ROAR_SUP_VITERBI", "ROAR_EMU_NO_DOA", "ROAR_EMU_NO_TWIN"):
+        for k in ("ROAR_SUP_VITERBI", "ROAR_EMU_NO_DOA", "ROAR_EMU_NO_TWIN", "ROAR_EMU_NO_FLAT"):
             monkeypatch.delenv(k, raising=False)
         base = hostemu.pyin(cfg, y, 329)
         assert (base[2] == 1.0).any()           # frames whose voiced probability clipped to 1: dense steps exist
-        for envs in (("ROAR_EMU_NO_DOA",), ("ROAR_EMU_NO_TWIN",), ("ROAR_EMU_NO_DOA", "ROAR_EMU_NO_TWIN")):
+        for envs in (("ROAR_EMU_NO_DOA",), ("ROAR_EMU_NO_TWIN",), ("ROAR_EMU_NO_FLAT",),
+                     ("ROAR_EMU_NO_DOA", "ROAR_EMU_NO_TWIN", "ROAR_EMU_NO_FLAT")):
             for k in envs:
                 monkeypatch.setenv(k, "1")
             alt = hostemu.pyin(cfg, y, 329)
